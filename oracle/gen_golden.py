@@ -1,0 +1,234 @@
+"""Generate tests/golden/*.npz by EXECUTING the unmodified reference on CPU.
+
+Generator-side only: run in the build container (``python oracle/gen_golden.py``) where
+/root/reference is mounted.  The reference ships no tests or golden vectors (SURVEY.md
+section 4), so these frozen input/output pairs are what pins ``oracle/mq_oracle.py``.
+Each case names the reference entry point it drives.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    from oracle._ref_import import import_reference
+
+    qu, hu = import_reference()
+    import torch
+
+    torch.manual_seed(42)  # drivers default --seed 42 (exam/quant_qwenvl.py:407)
+    torch.set_num_threads(1)
+    os.makedirs(OUT, exist_ok=True)
+
+    def rnd(*shape, scale=3.0, dtype=torch.float16):
+        x = torch.randn(*shape) * scale
+        # outlier channels to exercise the clamp, as in SURVEY.md 8(d)
+        if shape[-1] >= 64:
+            x[..., 7] *= 40
+            x[..., shape[-1] // 2 + 3] *= 25
+        return x.to(dtype)
+
+    # ---------------------------------------------------------------- 1. static act quant
+    # ActQuantizer.configure/forward (quant_utils.py:116-179) -> MinmaxObserver ->
+    # UniformQuantizer; three calibration batches, the last with last_calibrate.
+    case = {}
+    for tag, dtype, mode in (("f16", torch.float16, "layer_wise"),
+                             ("f32", torch.float32, "layer_wise"),
+                             ("f16cw", torch.float16, "channel_wise")):
+        q = qu.ActQuantizer()
+        q.configure(bits=8, sym=True, static=True, observer_type="minmax", calibration_mode=mode)
+        calib = [rnd(2, 24, 192, dtype=dtype) for _ in range(3)]
+        q.calibrate = True
+        for i, c in enumerate(calib):
+            if i == len(calib) - 1:
+                q.last_calibrate = True
+            out = q(c)
+            assert out is c
+        q.calibrate = False
+        q.quant = True
+        x = rnd(2, 40, 192, scale=4.0, dtype=dtype)
+        x[0, 0, :8] = torch.tensor([0.0, -0.0, 65504, -65504, 1e-4, -1e-4, 0.5, -0.5]).to(dtype)
+        y = q(x)
+        codes = q.quantizer.quant(x.float())
+        case[f"{tag}_calib"] = torch.stack(calib).numpy()
+        case[f"{tag}_x"] = x.numpy()
+        case[f"{tag}_scale"] = q.quantizer.scale.numpy()
+        case[f"{tag}_zp"] = q.quantizer.zero_point.numpy()
+        case[f"{tag}_min"] = np.asarray(q.observer.min_val.numpy())
+        case[f"{tag}_max"] = np.asarray(q.observer.max_val.numpy())
+        case[f"{tag}_codes"] = codes.numpy()
+        case[f"{tag}_y"] = y.numpy()
+    # half-way cases for round-half-even with an exactly representable scale
+    q = qu.ActQuantizer()
+    q.configure(bits=8, sym=True, static=True, observer_type="minmax")
+    q.quantizer.scale = torch.tensor(0.25, dtype=torch.float16)
+    q.quantizer.zero_point = torch.tensor(0, dtype=torch.int64)
+    q.quant = True
+    x = (torch.arange(-1100, 1100, dtype=torch.float32) * 0.125 / 4).to(torch.float16).reshape(1, -1, 8)
+    case["tie_x"] = x.numpy()
+    case["tie_scale"] = q.quantizer.scale.numpy()
+    case["tie_codes"] = q.quantizer.quant(x.float()).numpy()
+    case["tie_y"] = q(x).numpy()
+    np.savez_compressed(os.path.join(OUT, "act_quant.npz"), **case)
+
+    # ---------------------------------------------------------------- 2. minmax -> scale sweep
+    # MinmaxObserver.get_quantization_params (minmax.py:30-52) on hand-set statistics:
+    # every non-negative finite fp16 value as max (and its negation as min), plus fp32 samples.
+    from fake_quant.observer import build_observer
+    from fake_quant.bit_type import BIT_TYPE_DICT
+
+    ob = build_observer("minmax", "activation", BIT_TYPE_DICT["int8"], "channel_wise")
+    allpos = torch.arange(0, 0x7C00, dtype=torch.int32).to(torch.int16).view(torch.float16)
+    perm = torch.randperm(allpos.numel())
+    ob.max_val = allpos.clone()
+    ob.min_val = -allpos[perm]
+    s16, _ = ob.get_quantization_params()
+    mx32 = torch.rand(4096) * torch.logspace(-9, 4, 4096)
+    mn32 = -torch.rand(4096) * torch.logspace(-9, 4, 4096).flip(0)
+    ob.max_val, ob.min_val = mx32.clone(), mn32.clone()
+    s32, _ = ob.get_quantization_params()
+    np.savez_compressed(os.path.join(OUT, "minmax_params.npz"),
+                        max16=allpos.numpy(), min16=(-allpos[perm]).numpy(), scale16=s16.numpy(),
+                        max32=mx32.numpy(), min32=mn32.numpy(), scale32=s32.numpy())
+
+    # ---------------------------------------------------------------- 3. percentile observer
+    # PercentileObserver.update/get_quantization_params (percentile.py:26-79), 3 updates.
+    ob = build_observer("percentile", "activation", BIT_TYPE_DICT["int8"], "layer_wise")
+    pc = [rnd(1, 640, 192) for _ in range(3)]
+    stats = []
+    for c in pc:
+        ob.update(c)
+        stats.append([float(ob.min_val), float(ob.max_val)])
+    ps, _ = ob.get_quantization_params()
+    np.savez_compressed(os.path.join(OUT, "percentile.npz"), calib=torch.stack(pc).numpy(),
+                        stats=np.asarray(stats, dtype=np.float32), scale=ps.numpy())
+
+    # ---------------------------------------------------------------- 4. weight quantizer
+    # WeightQuantizer.configure/find_params/quantize (quant_utils.py:415-524), RTN and clip search
+    case = {}
+    lin = torch.nn.Linear(256, 96, bias=False)
+    W = lin.weight.data.clone()
+    W[3] *= 0  # all-zero row -> clamp(min=1e-5)
+    W[5, 17] = 0.9
+    for tag, dtype in (("f16", torch.float16), ("f32", torch.float32)):
+        for mse in (False, True):
+            wq = qu.WeightQuantizer()
+            wq.configure(4, perchannel=True, sym=True, mse=mse)
+            Wd = W.to(dtype)
+            wq.find_params(Wd)
+            fq = wq.quantize(Wd)
+            codes = torch.round(fq.float() / wq.scale)
+            case[f"{tag}_mse{int(mse)}_scale"] = wq.scale.numpy()
+            case[f"{tag}_mse{int(mse)}_fq"] = fq.numpy()
+            case[f"{tag}_mse{int(mse)}_codes"] = codes.numpy().astype(np.int8)
+        case[f"{tag}_W"] = W.to(dtype).numpy()
+    # ---- pack_i4 / unpack_i4 (quant_utils.py:61-94)
+    qi = torch.randint(-8, 8, (32, 64), dtype=torch.int32)
+    packed = qu.pack_i4(qi)
+    case["pack_q"] = qi.numpy()
+    case["pack_p"] = packed.numpy()
+    case["pack_u"] = qu.unpack_i4(packed).numpy()
+    np.savez_compressed(os.path.join(OUT, "weight_quant.npz"), **case)
+
+    # ---------------------------------------------------------------- 5. hadamard
+    case = {}
+    sizes = [64, 256, 4096, 8192, 11008, 13824, 14336, 19968, 3584, 5120, 1664, 344, 96, 1280]
+    ks = []
+    for n in sizes:
+        hk, k = hu.get_hadK(n)
+        ks.append(k)
+    case["hadk_sizes"] = np.asarray(sizes)
+    case["hadk_K"] = np.asarray(ks)
+    pads_in = [11008, 13696, 18944, 14336, 4096, 1000, 3584, 5120, 27392, 8192, 29568]
+    case["pad_in"] = np.asarray(pads_in)
+    case["pad_out"] = np.asarray([hu.auto_pad_size(n) for n in pads_in])
+    # pure-torch matmul_hadU in fp64 (hadamard_utils.py:79-100): the transform's anchor
+    for n in (256, 344, 11008 // 16):  # 688 = 172*4
+        x = torch.randn(3, n, dtype=torch.float64)
+        case[f"hadU_x_{n}"] = x.numpy()
+        case[f"hadU_y_{n}"] = hu.matmul_hadU(x).numpy()
+    # matmul_hadU_cuda with the FHT stub, fp16 in/out (hadamard_utils.py:115-128)
+    for n in (512, 344, 11008):
+        hk, k = hu.get_hadK(n)
+        x = rnd(4, n)
+        case[f"hadcuda_x_{n}"] = x.numpy()
+        case[f"hadcuda_y_{n}"] = hu.matmul_hadU_cuda(x, hk, k).numpy()
+        case[f"hadcuda_y32_{n}"] = hu.matmul_hadU_cuda(x.float(), hk, k).to(torch.float16).numpy()
+    # random_hadamard_matrix determinism (hadamard_utils.py:107-112)
+    torch.manual_seed(0)
+    case["rand_had_64"] = hu.random_hadamard_matrix(64, "cpu").numpy()
+    np.savez_compressed(os.path.join(OUT, "hadamard.npz"), **case)
+
+    # ---------------------------------------------------------------- 6. wrapper forward
+    # ActQuantWrapper.forward (quant_utils.py:330-391): plain, online Hadamard (K=1 and K=172),
+    # split.  W4 RTN weights, static int8 minmax activations calibrated on 2 batches.
+    torch.manual_seed(7)
+    case = {}
+    for tag, K_in, N_out, bias, had, split in (
+            ("plain", 256, 128, True, False, False),
+            ("had256", 256, 64, False, True, False),
+            ("had344", 344, 64, False, True, False),
+            ("split", 344, 64, False, True, True)):
+        lin = torch.nn.Linear(K_in, N_out, bias=bias).half()
+        if had:
+            hu_apply = lin.weight.data.float()
+            hk, k = hu.get_hadK(K_in)
+            lin.weight.data = hu.matmul_hadU_cuda(hu_apply, hk, k).half()
+        w = qu.ActQuantWrapper(lin)
+        if had:
+            w.online_full_had = True
+            w.had_K, w.K = hu.get_hadK(K_in)
+        if split:
+            w.split = True
+            w.split_weights()
+        # weight RTN as qwenvl_llm_rtn does (gptq/qwenvl_gptq_plus.py:450-481)
+        targets = [w.L2] if split else [w.module]
+        wscales = []
+        for t in targets:
+            wq = qu.WeightQuantizer()
+            wq.configure(4, perchannel=True, sym=True, mse=False)
+            wq.find_params(t.weight.data)
+            t.weight.data = wq.quantize(t.weight.data).to(torch.float16)
+            wscales.append(wq.scale.numpy())
+        w.quantizer.configure(bits=8, sym=True, static=True, observer_type="minmax")
+        w.quantizer.calibrate = True
+        for i in range(2):
+            if i == 1:
+                w.quantizer.last_calibrate = True
+            w(rnd(1, 32, K_in))
+        w.quantizer.calibrate = False
+        w.quantizer.quant = True
+        x = rnd(2, 16, K_in)
+        y = w(x.clone())
+        case[f"{tag}_x"] = x.numpy()
+        case[f"{tag}_y"] = y.detach().numpy()
+        case[f"{tag}_act_scale"] = w.quantizer.quantizer.scale.numpy()
+        if split:
+            case[f"{tag}_W"] = torch.cat([w.L1.weight.data.half(), w.L2.weight.data.half()], 1).numpy()
+        else:
+            case[f"{tag}_W"] = w.module.weight.data.numpy()
+        case[f"{tag}_wscale"] = wscales[0]
+        if bias:
+            case[f"{tag}_b"] = lin.bias.data.numpy()
+    np.savez_compressed(os.path.join(OUT, "wrapper.npz"), **case)
+
+    # ---------------------------------------------------------------- 7. dynamic per-token
+    q = qu.ActQuantizer()
+    q.configure(bits=8, sym=True, static=False)
+    x = rnd(2, 12, 192)
+    x[0, 3] = 0
+    q.find_params(x)
+    y = q(x)
+    np.savez_compressed(os.path.join(OUT, "dynamic.npz"), x=x.numpy(),
+                        scale=q.scale[..., 0].reshape(-1).numpy(), y=y.numpy())
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
