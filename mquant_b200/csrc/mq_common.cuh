@@ -1,0 +1,151 @@
+// Shared helpers for the mquant_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/mquant_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "mquant_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace mq {
+
+// ---- error plumbing (thread-local message, never throws across the ABI) -------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int num_sms();
+
+#define MQ_REQUIRE(cond, ...)       \
+  do {                              \
+    if (!(cond)) {                  \
+      mq::set_error(__VA_ARGS__);   \
+      return MQ_ERR_INVALID;        \
+    }                               \
+  } while (0)
+
+#define MQ_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t _e = (call);                            \
+    if (_e != cudaSuccess) return mq::cuda_fail(_e, #call); \
+  } while (0)
+
+#define MQ_LAUNCH_CHECK(name)                                      \
+  do {                                                             \
+    cudaError_t _e = cudaGetLastError();                           \
+    if (_e != cudaSuccess) return mq::cuda_fail(_e, name " launch"); \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- device helpers -------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// 128-bit streaming global accesses (read-once / write-once data: keep it out of L1)
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void stg_stream8(void* p, const uint2& v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// ---- the reference quantiser -----------------------------------------------------------------
+// code = clamp(rne(fl32(x / s)), lo, hi) with a TRUE fp32 division (uniform.py:28-31; zero_point
+// is 0 for the signed symmetric types that are reachable).
+//
+// A correctly rounded division per element would make these HBM-bound kernels issue-bound
+// (IEEE div ~8 instructions, F2I/FRND run at 1/8 rate).  Instead: r = x * fl(1/s) is within
+// 3*2^-24 relative of fl(x/s); rne(r) can differ from rne(fl(x/s)) only if r lies within that
+// distance of a half-integer.  Those (rare) elements are recomputed with __fdiv_rn, everything
+// else takes FMUL + clamp + magic-number rounding (1.5*2^23: FADD in round-to-nearest-even IS
+// rne, and the integer sits in the low mantissa bits).  The result is bit-identical to the
+// division for every input.
+#define MQ_RND_MAGIC 12582912.0f
+
+__device__ __forceinline__ float quant_code_exact(float x, float s, float lo, float hi) {
+  float q = rintf(__fdiv_rn(x, s));
+  return fminf(fmaxf(q, lo), hi);
+}
+
+// generic-width code as a float (fake-quant path, |hi| <= 2^19)
+__device__ __forceinline__ float quant_code(float x, float s, float inv, float lo, float hi) {
+  const float r = __fmul_rn(x, inv);
+  const float rc = fminf(fmaxf(r, lo), hi);
+  const float rr = __fadd_rn(__fadd_rn(rc, MQ_RND_MAGIC), -MQ_RND_MAGIC);
+  const float d = fabsf(fabsf(rc - rr) - 0.5f);
+  if (d <= fmaxf(fabsf(rc), 1.f) * 1e-6f) return quant_code_exact(x, s, lo, hi);
+  return rr;
+}
+
+// int8: returns the float whose low mantissa byte is the two's-complement code; `dist` is the
+// distance of the clamped quotient from the nearest half-integer
+__device__ __forceinline__ uint32_t q8_fast(float x, float inv, float& dist) {
+  const float r = __fmul_rn(x, inv);
+  const float rc = fminf(fmaxf(r, -128.f), 127.f);
+  const float t = __fadd_rn(rc, MQ_RND_MAGIC);
+  const float rr = __fadd_rn(t, -MQ_RND_MAGIC);
+  dist = fminf(dist, fabsf(fabsf(rc - rr) - 0.5f));
+  return __float_as_uint(t);
+}
+__device__ __forceinline__ uint32_t q8_exact(float x, float s) {
+  return (uint32_t)__float2int_rn(quant_code_exact(x, s, -128.f, 127.f));
+}
+
+__device__ __forceinline__ uint32_t pack4_lowbytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+// 8 halfs (one uint4) -> 8 floats
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8_f16(const float (&f)[8]) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+// 8 floats -> 8 int8 codes (one uint2); bit-exact w.r.t. quant_code_exact
+__device__ __forceinline__ uint2 quant8(const float (&f)[8], float s, float inv) {
+  float dist = 1.f;
+  uint32_t t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = q8_fast(f[i], inv, dist);
+  // 130 * 3 * 2^-24 = 2.3e-5 is the largest possible quotient error inside the clamp range
+  if (dist < 1e-4f) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = q8_exact(f[i], s);
+  }
+  uint2 r;
+  r.x = pack4_lowbytes(t[0], t[1], t[2], t[3]);
+  r.y = pack4_lowbytes(t[4], t[5], t[6], t[7]);
+  return r;
+}
+
+// fp16 round trip: the reference's rounding point after each Hadamard factor
+__device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
+
+#endif  // __CUDACC__
+
+}  // namespace mq

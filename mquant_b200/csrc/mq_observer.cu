@@ -1,0 +1,308 @@
+// Calibration observers (HBM-bound reductions over fp16 activations).
+//
+//   mq_observer_minmax       MinmaxObserver.update (fake_quant/observer/minmax.py:13-28)
+//   mq_observer_percentile   the two torch.quantile calls of PercentileObserver.update
+//                            (fake_quant/observer/percentile.py:31-32), exact
+//
+// minmax: algorithmic bytes = 2*M*C read, O(1) / O(C) written.  max/min of fp16 values are exact
+// and order independent, so the running statistics can be merged with atomics across CTAs,
+// streams and (after an NCCL allreduce-max) GPUs and stay bit-identical to the sequential
+// reference.  Running max >= 0 and running min <= 0 always hold (the reference folds 0 in on
+// the first update), which lets both be merged with integer atomics on the float bit pattern:
+//   max: non-negative floats order like signed ints      -> atomicMax(int)
+//   min: non-positive floats order like unsigned ints    -> atomicMax(unsigned) (more negative
+//        = larger pattern; +0.0 = 0 is the identity)
+#include "mq_common.cuh"
+
+namespace mq {
+
+__device__ __forceinline__ void merge_max(float* addr, float v) {
+  if (v > 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+__device__ __forceinline__ void merge_min(float* addr, float v) {
+  if (v < 0.f) atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// layer_wise: one scalar pair for the whole [M, C] tensor
+__global__ void __launch_bounds__(256)
+minmax_tensor_kernel(const __half* __restrict__ x, int64_t ldx, int64_t M, int C, float* __restrict__ io) {
+  const int chunks_per_row = C >> 3;
+  const int64_t total = M * chunks_per_row;
+  __half2 mx = __float2half2_rn(0.f), mn = __float2half2_rn(0.f);
+  const bool contiguous = (ldx == C);
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < total;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const __half* p;
+    if (contiguous) {
+      p = x + c * 8;
+    } else {
+      const int64_t m = c / chunks_per_row;
+      p = x + m * ldx + ((c - m * chunks_per_row) << 3);
+    }
+    const uint4 v = ldg_stream(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mx = __hmax2(mx, h[i]);
+      mn = __hmin2(mn, h[i]);
+    }
+  }
+  float fmx = fmaxf(__low2float(mx), __high2float(mx));
+  float fmn = fminf(__low2float(mn), __high2float(mn));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    fmx = fmaxf(fmx, __shfl_xor_sync(0xffffffffu, fmx, o));
+    fmn = fminf(fmn, __shfl_xor_sync(0xffffffffu, fmn, o));
+  }
+  __shared__ float smx[8], smn[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    smx[w] = fmx;
+    smn[w] = fmn;
+  }
+  __syncthreads();
+  if (w == 0) {
+    fmx = lane < 8 ? smx[lane] : 0.f;
+    fmn = lane < 8 ? smn[lane] : 0.f;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      fmx = fmaxf(fmx, __shfl_xor_sync(0xffffffffu, fmx, o));
+      fmn = fminf(fmn, __shfl_xor_sync(0xffffffffu, fmn, o));
+    }
+    if (lane == 0) {
+      merge_min(io + 0, fmn);
+      merge_max(io + 1, fmx);
+    }
+  }
+}
+
+// channel_wise: io = {min[C], max[C]}.  blockIdx.x -> 2048-channel slab (256 threads x 8
+// channels), blockIdx.y -> row slice; each thread keeps its 8 channels in registers.
+__global__ void __launch_bounds__(256)
+minmax_channel_kernel(const __half* __restrict__ x, int64_t ldx, int64_t M, int C, float* __restrict__ io) {
+  const int col = (blockIdx.x * 256 + threadIdx.x) << 3;
+  if (col >= C) return;
+  __half2 mx[4], mn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) mx[i] = mn[i] = __float2half2_rn(0.f);
+  for (int64_t m = blockIdx.y; m < M; m += gridDim.y) {
+    const uint4 v = ldg_stream(x + m * ldx + col);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mx[i] = __hmax2(mx[i], h[i]);
+      mn[i] = __hmin2(mn[i], h[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    merge_min(io + col + 2 * i, __low2float(mn[i]));
+    merge_min(io + col + 2 * i + 1, __high2float(mn[i]));
+    merge_max(io + C + col + 2 * i, __low2float(mx[i]));
+    merge_max(io + C + col + 2 * i + 1, __high2float(mx[i]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Percentile: exact order statistics of fp16 data by counting.
+//   key(x)  = monotone 16-bit map of the fp16 pattern (negative: ~bits, non-negative: bits|0x8000)
+//   pass 1  : 65536-bin histogram of keys.  Per-CTA privatisation does not fit (256 KB), so each
+//             CTA histograms the TOP 12 bits in shared memory (4096 bins, warp-aggregated) and the
+//             fine 16-bit histogram is built only for the coarse bins that contain a wanted rank
+//             (pass 2 re-reads the tensor: 4*M*C bytes total, as SURVEY.md 8(d) budgets).
+//   finish  : ranks floor/ceil(q*(n-1)) -> values -> torch's lerp, in fp32 (ATen quantile).
+// workspace layout (uint32): coarse[4096] | fine[4][16] | sel[4] (selected coarse bins)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned key16(unsigned short b) {
+  return (b & 0x8000u) ? (unsigned)(~b & 0xffffu) : (unsigned)(b | 0x8000u);
+}
+__device__ __forceinline__ float key_to_float(unsigned k) {
+  const unsigned short b = (k & 0x8000u) ? (unsigned short)(k & 0x7fffu) : (unsigned short)(~k & 0xffffu);
+  return __half2float(__ushort_as_half(b));
+}
+
+constexpr int kCoarseBins = 4096;
+constexpr int kPctWords = kCoarseBins + 4 * 16 + 8;
+
+__global__ void __launch_bounds__(256)
+pct_coarse_kernel(const __half* __restrict__ x, int64_t ldx, int64_t M, int C, unsigned* __restrict__ ws) {
+  __shared__ unsigned hist[kCoarseBins];
+  for (int i = threadIdx.x; i < kCoarseBins; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int chunks_per_row = C >> 3;
+  const int64_t total = M * chunks_per_row;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < total;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = c / chunks_per_row;
+    const uint4 v = ldg_stream(x + m * ldx + ((c - m * chunks_per_row) << 3));
+    const unsigned short* h = reinterpret_cast<const unsigned short*>(&v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&hist[key16(h[i]) >> 4], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kCoarseBins; i += blockDim.x)
+    if (hist[i]) atomicAdd(&ws[i], hist[i]);
+}
+
+// ranks wanted: r[0..3] = floor/ceil of the low rank, floor/ceil of the high rank
+__device__ __forceinline__ void wanted_ranks(int64_t n, double alpha, int64_t (&r)[4], float (&w)[2]) {
+  // torch.quantile: q as fp32 scalar, rank = q * (n - 1) in fp32
+  const float q_hi = (float)alpha;
+  const float q_lo = (float)(1.0 - alpha);
+  const float nm1 = (float)(n - 1);
+  const float rk_lo = __fmul_rn(q_lo, nm1), rk_hi = __fmul_rn(q_hi, nm1);
+  r[0] = (int64_t)floorf(rk_lo);
+  r[1] = (int64_t)ceilf(rk_lo);
+  r[2] = (int64_t)floorf(rk_hi);
+  r[3] = (int64_t)ceilf(rk_hi);
+  w[0] = rk_lo - floorf(rk_lo);
+  w[1] = rk_hi - floorf(rk_hi);
+}
+
+__global__ void pct_select_kernel(unsigned* __restrict__ ws, int64_t n, double alpha) {
+  // single thread: 4096-bin scan (negligible)
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int64_t r[4];
+  float w[2];
+  wanted_ranks(n, alpha, r, w);
+  unsigned* sel = ws + kCoarseBins + 64;
+  int64_t cum = 0;
+  int found = 0;
+  for (int b = 0; b < kCoarseBins && found < 4; ++b) {
+    const int64_t next = cum + ws[b];
+    while (found < 4 && r[found] < next) {
+      sel[found] = (unsigned)b;
+      // rank of the wanted element inside this coarse bin
+      sel[4 + found] = (unsigned)(r[found] - cum);
+      ++found;
+    }
+    cum = next;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pct_fine_kernel(const __half* __restrict__ x, int64_t ldx, int64_t M, int C, unsigned* __restrict__ ws) {
+  __shared__ unsigned fine[4][16];
+  if (threadIdx.x < 64) fine[threadIdx.x >> 4][threadIdx.x & 15] = 0;
+  const unsigned* sel = ws + kCoarseBins + 64;
+  const unsigned s0 = sel[0], s1 = sel[1], s2 = sel[2], s3 = sel[3];
+  __syncthreads();
+  const int chunks_per_row = C >> 3;
+  const int64_t total = M * chunks_per_row;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < total;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = c / chunks_per_row;
+    const uint4 v = ldg_stream(x + m * ldx + ((c - m * chunks_per_row) << 3));
+    const unsigned short* h = reinterpret_cast<const unsigned short*>(&v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const unsigned k = key16(h[i]);
+      const unsigned cb = k >> 4;
+      // the four selected bins are the extreme tails: almost every element skips all four
+      if (cb == s0) atomicAdd(&fine[0][k & 15], 1u);
+      if (cb == s1) atomicAdd(&fine[1][k & 15], 1u);
+      if (cb == s2) atomicAdd(&fine[2][k & 15], 1u);
+      if (cb == s3) atomicAdd(&fine[3][k & 15], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const unsigned v = fine[threadIdx.x >> 4][threadIdx.x & 15];
+    if (v) atomicAdd(&ws[kCoarseBins + threadIdx.x], v);
+  }
+}
+
+__global__ void pct_finish_kernel(const unsigned* __restrict__ ws, int64_t n, double alpha,
+                                  float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int64_t r[4];
+  float w[2];
+  wanted_ranks(n, alpha, r, w);
+  const unsigned* sel = ws + kCoarseBins + 64;
+  float val[4];
+  for (int i = 0; i < 4; ++i) {
+    const unsigned* f = ws + kCoarseBins + 16 * i;
+    unsigned want = sel[4 + i], cum = 0;
+    unsigned k = 15;
+    for (unsigned b = 0; b < 16; ++b) {
+      cum += f[b];
+      if (want < cum) {
+        k = b;
+        break;
+      }
+    }
+    val[i] = key_to_float((sel[i] << 4) | k);
+  }
+  // at::lerp: w < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w), each op one fp32 rounding
+  for (int j = 0; j < 2; ++j) {
+    const float lo = val[2 * j], hi = val[2 * j + 1];
+    const float diff = __fsub_rn(hi, lo);
+    out[j] = (w[j] < 0.5f) ? __fadd_rn(lo, __fmul_rn(w[j], diff))
+                           : __fsub_rn(hi, __fmul_rn(diff, __fsub_rn(1.f, w[j])));
+  }
+}
+
+}  // namespace mq
+
+extern "C" int mq_observer_minmax(const void* x, int64_t ldx, int64_t M, int C, int per_channel,
+                                  float* minmax_io, void* stream) {
+  using namespace mq;
+  MQ_REQUIRE(x && minmax_io, "mq_observer_minmax: null pointer");
+  MQ_REQUIRE(M >= 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldx >= C,
+             "mq_observer_minmax: need C%%8==0 and ldx%%8==0 (C=%d ldx=%lld)", C, (long long)ldx);
+  MQ_REQUIRE(aligned16(x), "mq_observer_minmax: x must be 16-byte aligned");
+  if (M == 0) return MQ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!per_channel) {
+    const int64_t chunks = M * (C / 8);
+    int64_t blocks = (chunks + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    minmax_tensor_kernel<<<(int)blocks, 256, 0, st>>>((const __half*)x, ldx, M, C, minmax_io);
+  } else {
+    const int slabs = (C + 2047) / 2048;
+    int64_t slices = ((int64_t)num_sms() * 8 + slabs - 1) / slabs;
+    if (slices > M) slices = M;
+    if (slices > 65535) slices = 65535;
+    dim3 grid(slabs, (unsigned)slices);
+    minmax_channel_kernel<<<grid, 256, 0, st>>>((const __half*)x, ldx, M, C, minmax_io);
+  }
+  MQ_LAUNCH_CHECK("minmax kernel");
+  return MQ_OK;
+}
+
+extern "C" size_t mq_observer_percentile_workspace(void) { return sizeof(unsigned) * mq::kPctWords; }
+
+extern "C" int mq_observer_percentile(const void* x, int64_t ldx, int64_t M, int C, double alpha, float* out,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace mq;
+  MQ_REQUIRE(x && out && workspace, "mq_observer_percentile: null pointer");
+  MQ_REQUIRE(M > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldx >= C,
+             "mq_observer_percentile: need M>0, C%%8==0, ldx%%8==0 (C=%d)", C);
+  MQ_REQUIRE(aligned16(x), "mq_observer_percentile: x must be 16-byte aligned");
+  MQ_REQUIRE(alpha > 0.5 && alpha < 1.0, "mq_observer_percentile: alpha=%f outside (0.5, 1)", alpha);
+  if (workspace_bytes < mq_observer_percentile_workspace()) {
+    set_error("mq_observer_percentile: workspace %zu < %zu bytes", workspace_bytes,
+              mq_observer_percentile_workspace());
+    return MQ_ERR_WORKSPACE;
+  }
+  // torch.quantile forms the rank in fp32: beyond 2^24 elements the reference itself leaves this
+  // branch (percentile.py:33-43 numpy fallback); we keep the same arithmetic at any size.
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* ws = (unsigned*)workspace;
+  MQ_CUDA(cudaMemsetAsync(ws, 0, mq_observer_percentile_workspace(), st));
+  const int64_t n = M * (int64_t)C;
+  const int64_t chunks = M * (C / 8);
+  int64_t blocks = (chunks + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  pct_coarse_kernel<<<(int)blocks, 256, 0, st>>>((const __half*)x, ldx, M, C, ws);
+  MQ_LAUNCH_CHECK("pct_coarse_kernel");
+  pct_select_kernel<<<1, 32, 0, st>>>(ws, n, alpha);
+  MQ_LAUNCH_CHECK("pct_select_kernel");
+  pct_fine_kernel<<<(int)blocks, 256, 0, st>>>((const __half*)x, ldx, M, C, ws);
+  MQ_LAUNCH_CHECK("pct_fine_kernel");
+  pct_finish_kernel<<<1, 32, 0, st>>>(ws, n, alpha, out);
+  MQ_LAUNCH_CHECK("pct_finish_kernel");
+  return MQ_OK;
+}

@@ -1,0 +1,218 @@
+// Activation quantisation kernels (HBM-bound, one pass).
+//
+//   mq_act_quant_i8          static INT8, MSQ two-scale select, zero-pad, RMS split
+//   mq_act_fake_quant_f16    quant -> dequant in one pass (drop-in for BaseQuantizer.forward)
+//   mq_act_quant_i8_dynamic  per-token symmetric scales + codes (ActQuantizer.find_params)
+//
+// Algorithmic bytes per element: 2 read + 1 written (codes) or 2 + 2 (fake quant).
+// Each thread moves 16 halfs (two 128-bit loads) and writes one 128-bit vector of codes, so
+// a warp reads 1 KB and writes 512 B fully coalesced; grid = a multiple of the SM count,
+// grid-stride over (row, 16-column chunk).
+#include "mq_common.cuh"
+
+namespace mq {
+
+__global__ void __launch_bounds__(256)
+act_quant_i8_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* __restrict__ q,
+                    float* __restrict__ srow_out, __half* __restrict__ x0_out,
+                    const uint8_t* __restrict__ modality, const float* __restrict__ scales,
+                    int64_t M, int n_in, int n_out, unsigned flags) {
+  const int chunks_per_row = n_out >> 4;
+  const int64_t total = M * chunks_per_row;
+  const float s_text = __ldg(scales), s_vis = __ldg(scales + 1);
+  const float inv_text = __frcp_rn(s_text), inv_vis = __frcp_rn(s_vis);
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < total;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = c / chunks_per_row;
+    const int col = (int)(c - m * chunks_per_row) << 4;
+    const bool vis = (modality != nullptr && modality[m] != 0);
+    const float s = vis ? s_vis : s_text;
+    const float inv = vis ? inv_vis : inv_text;
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    const __half* xr = x + m * ldx + col;
+    float f[8];
+    if (col + 8 <= n_in) {
+      uint4 v = ldg_stream(xr);
+      unpack8(v, f);
+      uint2 r = quant8(f, s, inv);
+      out.x = r.x;
+      out.y = r.y;
+      if (col == 0) {
+        if (flags & MQ_FLAG_SPLIT) {
+          x0_out[m] = reinterpret_cast<const __half*>(&v)[0];
+          out.x &= 0xffffff00u;
+        }
+        if (srow_out != nullptr) srow_out[m] = s;
+      }
+    }
+    if (col + 16 <= n_in) {
+      uint4 v = ldg_stream(xr + 8);
+      unpack8(v, f);
+      uint2 r = quant8(f, s, inv);
+      out.z = r.x;
+      out.w = r.y;
+    }
+    stg_stream(q + m * (int64_t)n_out + col, out);
+  }
+}
+
+// scale_mode 0: per-token scale by modality; 1: per-channel scale array
+template <int kScaleMode>
+__global__ void __launch_bounds__(256)
+act_fake_quant_kernel(const __half* __restrict__ x, int64_t ldx, __half* __restrict__ y, int64_t ldy,
+                      const uint8_t* __restrict__ modality, const float* __restrict__ scales,
+                      float lo, float hi, int64_t M, int C) {
+  const int chunks_per_row = C >> 3;
+  const int64_t total = M * chunks_per_row;
+  float s_text = 0.f, s_vis = 0.f;
+  if (kScaleMode == 0) {
+    s_text = __ldg(scales);
+    s_vis = __ldg(scales + 1);
+  }
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < total;
+       c += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = c / chunks_per_row;
+    const int col = (int)(c - m * chunks_per_row) << 3;
+    uint4 v = ldg_stream(x + m * ldx + col);
+    float f[8];
+    unpack8(v, f);
+    if (kScaleMode == 0) {
+      const float s = (modality != nullptr && modality[m] != 0) ? s_vis : s_text;
+      const float inv = __frcp_rn(s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = __fmul_rn(quant_code(f[i], s, inv, lo, hi), s);
+    } else {
+      const float4 sa = __ldg(reinterpret_cast<const float4*>(scales + col));
+      const float4 sb = __ldg(reinterpret_cast<const float4*>(scales + col + 4));
+      const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = __fmul_rn(quant_code(f[i], sc[i], __frcp_rn(sc[i]), lo, hi), sc[i]);
+    }
+    stg_stream(y + m * ldy + col, pack8_f16(f));
+  }
+}
+
+// One warp per token row: pass 1 min/max (row stays in L1/L2), pass 2 quantise.
+__global__ void __launch_bounds__(256)
+act_quant_i8_dynamic_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* __restrict__ q,
+                            float* __restrict__ srow_out, int64_t M, int n_in, int n_out,
+                            float clip_ratio) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t m = warp; m < M; m += nwarps) {
+    const __half* xr = x + m * ldx;
+    __half2 mx = __float2half2_rn(0.f), mn = __float2half2_rn(0.f);
+    for (int col = lane << 3; col < n_in; col += 256) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + col));
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        mx = __hmax2(mx, h[i]);
+        mn = __hmin2(mn, h[i]);
+      }
+    }
+    float fmx = fmaxf(__low2float(mx), __high2float(mx));
+    float fmn = fminf(__low2float(mn), __high2float(mn));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      fmx = fmaxf(fmx, __shfl_xor_sync(0xffffffffu, fmx, o));
+      fmn = fminf(fmn, __shfl_xor_sync(0xffffffffu, fmn, o));
+    }
+    // quant_utils.py:240-247: xmin/xmax (with 0) * clip_ratio in fp32, xmax = max(|xmin|, xmax),
+    // scale = xmax / maxq, all-zero rows -> 1
+    const float xmin = __fmul_rn(fmn, clip_ratio), xmax0 = __fmul_rn(fmx, clip_ratio);
+    const float xmax = fmaxf(fabsf(xmin), xmax0);
+    const float s = (xmax == 0.f) ? 1.f : __fdiv_rn(xmax, 127.f);
+    if (lane == 0) srow_out[m] = s;
+    const float inv = __frcp_rn(s);
+    for (int col = lane << 4; col < n_out; col += 512) {
+      uint4 out = make_uint4(0u, 0u, 0u, 0u);
+      float f[8];
+      if (col + 8 <= n_in) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + col));
+        unpack8(v, f);
+        uint2 r = quant8(f, s, inv);
+        out.x = r.x;
+        out.y = r.y;
+      }
+      if (col + 16 <= n_in) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + col + 8));
+        unpack8(v, f);
+        uint2 r = quant8(f, s, inv);
+        out.z = r.x;
+        out.w = r.y;
+      }
+      stg_stream(q + m * (int64_t)n_out + col, out);
+    }
+  }
+}
+
+static int grid_for(int64_t work_items, int threads, int per_sm) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)num_sms() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace mq
+
+extern "C" int mq_act_quant_i8(const void* x, int64_t ldx, int8_t* q, float* srow_out, void* x0_out,
+                               const uint8_t* modality, const float* scales, int64_t M, int n_in,
+                               int n_out, unsigned flags, void* stream) {
+  MQ_REQUIRE(x && q && scales, "mq_act_quant_i8: null pointer");
+  MQ_REQUIRE(M >= 0 && n_in > 0 && n_out >= n_in, "mq_act_quant_i8: bad shape M=%lld n_in=%d n_out=%d",
+             (long long)M, n_in, n_out);
+  MQ_REQUIRE(n_in % 8 == 0 && n_out % 16 == 0 && ldx % 8 == 0 && ldx >= n_in,
+             "mq_act_quant_i8: need n_in%%8==0, n_out%%16==0, ldx%%8==0 (n_in=%d n_out=%d ldx=%lld)", n_in,
+             n_out, (long long)ldx);
+  MQ_REQUIRE(mq::aligned16(x) && mq::aligned16(q), "mq_act_quant_i8: pointers must be 16-byte aligned");
+  MQ_REQUIRE(!(flags & MQ_FLAG_SPLIT) || x0_out, "mq_act_quant_i8: MQ_FLAG_SPLIT needs x0_out");
+  if (M == 0) return MQ_OK;
+  const int64_t chunks = M * (n_out / 16);
+  const int grid = mq::grid_for(chunks, 256, 8);
+  mq::act_quant_i8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, ldx, q, srow_out, (__half*)x0_out, modality, scales, M, n_in, n_out, flags);
+  MQ_LAUNCH_CHECK("act_quant_i8_kernel");
+  return MQ_OK;
+}
+
+extern "C" int mq_act_fake_quant_f16(const void* x, int64_t ldx, void* y, int64_t ldy,
+                                     const uint8_t* modality, const float* scales, int scale_mode,
+                                     int bits, int64_t M, int C, void* stream) {
+  MQ_REQUIRE(x && y && scales, "mq_act_fake_quant_f16: null pointer");
+  MQ_REQUIRE(M >= 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C,
+             "mq_act_fake_quant_f16: need C%%8==0 and 8-element aligned strides (C=%d)", C);
+  MQ_REQUIRE(mq::aligned16(x) && mq::aligned16(y), "mq_act_fake_quant_f16: pointers must be 16-byte aligned");
+  MQ_REQUIRE(bits >= 2 && bits <= 24, "mq_act_fake_quant_f16: bits=%d out of range", bits);
+  MQ_REQUIRE(scale_mode == 0 || scale_mode == 1, "mq_act_fake_quant_f16: scale_mode=%d", scale_mode);
+  if (M == 0) return MQ_OK;
+  const float lo = -(float)(1 << (bits - 1)), hi = (float)((1 << (bits - 1)) - 1);
+  const int64_t chunks = M * (C / 8);
+  const int grid = mq::grid_for(chunks, 256, 8);
+  if (scale_mode == 0)
+    mq::act_fake_quant_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, ldx, (__half*)y, ldy, modality, scales, lo, hi, M, C);
+  else
+    mq::act_fake_quant_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, ldx, (__half*)y, ldy, modality, scales, lo, hi, M, C);
+  MQ_LAUNCH_CHECK("act_fake_quant_kernel");
+  return MQ_OK;
+}
+
+extern "C" int mq_act_quant_i8_dynamic(const void* x, int64_t ldx, int8_t* q, float* srow_out, int64_t M,
+                                       int n_in, int n_out, float clip_ratio, void* stream) {
+  MQ_REQUIRE(x && q && srow_out, "mq_act_quant_i8_dynamic: null pointer");
+  MQ_REQUIRE(M >= 0 && n_in > 0 && n_out >= n_in && n_in % 8 == 0 && n_out % 16 == 0 && ldx % 8 == 0 &&
+                 ldx >= n_in,
+             "mq_act_quant_i8_dynamic: bad shape/alignment (n_in=%d n_out=%d ldx=%lld)", n_in, n_out,
+             (long long)ldx);
+  MQ_REQUIRE(mq::aligned16(x) && mq::aligned16(q), "mq_act_quant_i8_dynamic: pointers must be 16-byte aligned");
+  if (M == 0) return MQ_OK;
+  const int grid = mq::grid_for(M * 32, 256, 8);
+  mq::act_quant_i8_dynamic_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, q, srow_out,
+                                                                          M, n_in, n_out, clip_ratio);
+  MQ_LAUNCH_CHECK("act_quant_i8_dynamic_kernel");
+  return MQ_OK;
+}

@@ -1,0 +1,100 @@
+"""Multi-GPU plumbing for the two places the path shards.
+
+* Calibration: samples are split across ranks; every rank runs the observers on its shard; the
+  running min/max of all MinmaxObservers are merged with ONE allreduce(MAX) over a packed fp32
+  buffer [max ; -min] (a few KB -- latency bound, NCCL over NVLink).  max/min are associative,
+  commutative and exact, so the merged statistics (and the scales every rank then derives) are
+  bit-identical to single-GPU sequential calibration.  Percentile/EMA observers are order
+  dependent and are NOT merged (replicas only).
+* Batched prefill: token batches are data parallel with replicated weights and no collective.
+
+One process per GPU (torchrun); works on the gloo backend with CPU tensors for the CPU tests.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .observer.minmax import MinmaxObserver
+from .quant_utils import ActQuantWrapper, find_qlayers
+
+
+def shard_indices(n_items: int, rank: int, world: int):
+    """Round-robin shard of calibration samples."""
+    return list(range(rank, n_items, world))
+
+
+def _minmax_observers(model):
+    obs = []
+    for name, layer in sorted(find_qlayers(model, layers=[ActQuantWrapper]).items()):
+        q = layer.quantizer
+        if not getattr(q, "static", False):
+            continue
+        for o in (q.observer, getattr(q, "observer_visual", None)):
+            if isinstance(o, MinmaxObserver):
+                obs.append((name, o))
+    return obs
+
+
+def pack_minmax(states):
+    """[{min..., max...}] fp32 buffers -> one flat [max ; -min] buffer (so a single MAX merges both)."""
+    parts = []
+    for st in states:
+        half = st.numel() // 2
+        parts.append(st[half:])
+        parts.append(-st[:half])
+    return torch.cat(parts) if parts else torch.zeros(0)
+
+
+def unpack_minmax(flat, states):
+    off = 0
+    for st in states:
+        half = st.numel() // 2
+        st[half:] = flat[off:off + half]
+        off += half
+        st[:half] = -flat[off:off + half]
+        off += half
+
+
+def merge_observer_states(states, group=None):
+    """allreduce(MAX) of a list of MinmaxObserver state buffers, in place."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return states
+    flat = pack_minmax(states).contiguous()
+    if flat.numel():
+        dist.all_reduce(flat, op=dist.ReduceOp.MAX, group=group)
+        unpack_minmax(flat, states)
+    return states
+
+
+def merge_calibration(model, group=None, channels_hint=None):
+    """Merge every static MinmaxObserver of `model` across ranks and refresh its min/max views.
+    Observers that saw no data on a rank get a zero state of the right size first (needs one rank
+    to have seen data: sizes are agreed via an allreduce(MAX) of the element counts)."""
+    obs = _minmax_observers(model)
+    if not obs:
+        return 0
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    dev = None
+    for _, o in obs:
+        if o.state is not None:
+            dev = o.state.device
+            break
+    if dev is None:
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    sizes = torch.tensor([0 if o.state is None else o.state.numel() for _, o in obs], dtype=torch.int64, device=dev)
+    if distributed:
+        dist.all_reduce(sizes, op=dist.ReduceOp.MAX, group=group)
+    live = []
+    for (name, o), n in zip(obs, sizes.tolist()):
+        if n == 0:
+            continue
+        if o.state is None:
+            o.state = torch.zeros(n, dtype=torch.float32, device=dev)
+            o._dtype = o._dtype or torch.float16
+            o._channels = n // 2
+        live.append(o)
+    merge_observer_states([o.state for o in live], group)
+    for o in live:
+        o._refresh()
+    return len(live)

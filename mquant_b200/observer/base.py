@@ -1,0 +1,34 @@
+"""Observer base (mirror of fake_quant/observer/base.py:5-35)."""
+import torch
+
+
+class BaseObserver:
+    def __init__(self, module_type, bit_type, calibration_mode):
+        self.module_type = module_type
+        self.bit_type = bit_type
+        self.calibration_mode = calibration_mode
+        self.max_val = None
+        self.min_val = None
+        self.eps = torch.finfo(torch.float32).eps
+
+    def update(self, v):
+        raise NotImplementedError
+
+    def get_quantization_params(self, *args, **kwargs):
+        raise NotImplementedError
+
+    # shared by minmax / percentile: reference minmax.py:30-52 == percentile.py:57-79
+    def _params_from_minmax(self):
+        max_val, min_val = self.max_val, self.min_val
+        qmax, qmin = self.bit_type.upper_bound, self.bit_type.lower_bound
+        if self.symmetric:
+            # evaluated in the dtype of the statistics (fp16 for fp16 activations)
+            scale = torch.max(torch.abs(min_val / qmin), torch.abs(max_val / qmax))
+            scale.clamp_(self.eps)
+            zero_point = torch.zeros_like(max_val, dtype=torch.int64)
+        else:
+            scale = (max_val - min_val) / float(qmax - qmin)
+            scale.clamp_(self.eps)
+            zero_point = qmin - torch.round(min_val / scale)
+            zero_point.clamp_(qmin, qmax)
+        return scale, zero_point

@@ -1,0 +1,49 @@
+"""MinmaxObserver on the GPU (mirror of fake_quant/observer/minmax.py:7-52).
+
+The running statistics live in one fp32 device buffer that mq_observer_minmax merges into with
+atomics ({min, max} or {min[C], max[C]}).  max/min of fp16 values are exact, so the buffer can
+also be merged across ranks with allreduce(MAX) on {max, -min} (mquant_b200.dist) and stays
+bit-identical to the reference's sequential update.
+"""
+import torch
+
+from .. import ops
+from .base import BaseObserver
+
+
+class MinmaxObserver(BaseObserver):
+    def __init__(self, module_type, bit_type, calibration_mode):
+        super().__init__(module_type, bit_type, calibration_mode)
+        self.symmetric = self.bit_type.signed
+        self.state = None      # fp32 device buffer, see above
+        self._dtype = None     # dtype of the observed activations (statistics keep it)
+        self._channels = None
+
+    def _per_channel(self):
+        return self.calibration_mode != "layer_wise"
+
+    def update(self, v):
+        if self.module_type != "activation":
+            raise NotImplementedError("mquant_b200 observes activations only")
+        v = v.detach()
+        if v.dim() == 4:
+            v = v.permute(0, 2, 3, 1)
+        C = v.shape[-1]
+        if self.state is None:
+            n = 2 * C if self._per_channel() else 2
+            self.state = torch.zeros(n, dtype=torch.float32, device=v.device)
+            self._dtype, self._channels = v.dtype, C
+        ops.observer_minmax(v, self.state, per_channel=self._per_channel())
+        self._refresh()
+
+    def _refresh(self):
+        if self._per_channel():
+            C = self._channels
+            self.min_val = self.state[:C].to(self._dtype)
+            self.max_val = self.state[C:].to(self._dtype)
+        else:
+            self.min_val = self.state[0].to(self._dtype)
+            self.max_val = self.state[1].to(self._dtype)
+
+    def get_quantization_params(self, *args, **kwargs):
+        return self._params_from_minmax()

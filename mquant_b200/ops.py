@@ -1,0 +1,212 @@
+"""Thin torch-facing wrappers over the C ABI: device pointers in, torch tensors out.
+
+torch is plumbing here (allocation, streams); all arithmetic happens in libmquant_b200.so.
+Every op requires CUDA tensors and raises otherwise -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import MQ_FLAG_FP32_HAD, MQ_FLAG_SPLIT, check, lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MQuantLibraryError("mquant_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _as_rows(x):
+    """[..., C] -> 2-D view with unit column stride (copy only if the layout forces it)."""
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0):
+        x2 = x2.contiguous()
+    return x2
+
+
+def _ld(x2):
+    return x2.stride(0) if x2.shape[0] > 1 else max(x2.shape[1], x2.stride(0))
+
+
+def make_scales(s_text, s_visual=None, device=None):
+    """float32[2] device tensor {s_text, s_visual} from python floats or 0-dim tensors."""
+    if s_visual is None:
+        s_visual = s_text
+    vals = []
+    for s in (s_text, s_visual):
+        if torch.is_tensor(s):
+            vals.append(s.detach().to(device=device, dtype=torch.float32).reshape(()))
+        else:
+            vals.append(torch.tensor(float(s), dtype=torch.float32, device=device))
+    return torch.stack(vals)
+
+
+def act_quant_i8(x, scales, modality=None, n_out=None, split=False, want_row_scales=True):
+    """mq_act_quant_i8.  x: [..., C] fp16.  Returns (codes int8 [M, n_out], s_row fp32 [M] | None,
+    x0 fp16 [M] | None)."""
+    _need_cuda(x, scales, modality)
+    assert x.dtype == torch.float16, "activations must be fp16"
+    x2 = _as_rows(x)
+    M, C = x2.shape
+    n_out = C if n_out is None else n_out
+    q = torch.empty((M, n_out), dtype=torch.int8, device=x.device)
+    srow = torch.empty((M,), dtype=torch.float32, device=x.device) if want_row_scales else None
+    x0 = torch.empty((M,), dtype=torch.float16, device=x.device) if split else None
+    check(lib().mq_act_quant_i8(_ptr(x2), _ld(x2), _ptr(q), _ptr(srow), _ptr(x0), _ptr(modality),
+                                _ptr(scales), M, C, n_out, MQ_FLAG_SPLIT if split else 0, _stream()),
+          "mq_act_quant_i8")
+    return q, srow, x0
+
+
+def act_fake_quant(x, scales, modality=None, bits=8, per_channel=False, out=None):
+    """mq_act_fake_quant_f16: quant->dequant, same shape/dtype as x."""
+    _need_cuda(x, scales, modality)
+    assert x.dtype == torch.float16
+    x2 = _as_rows(x)
+    M, C = x2.shape
+    y = torch.empty((M, C), dtype=torch.float16, device=x.device) if out is None else out.reshape(M, C)
+    check(lib().mq_act_fake_quant_f16(_ptr(x2), _ld(x2), _ptr(y), _ld(y), _ptr(modality), _ptr(scales),
+                                      1 if per_channel else 0, bits, M, C, _stream()),
+          "mq_act_fake_quant_f16")
+    return y.reshape(x.shape)
+
+
+def act_quant_i8_dynamic(x, clip_ratio=1.0, n_out=None):
+    _need_cuda(x)
+    assert x.dtype == torch.float16
+    x2 = _as_rows(x)
+    M, C = x2.shape
+    n_out = C if n_out is None else n_out
+    q = torch.empty((M, n_out), dtype=torch.int8, device=x.device)
+    srow = torch.empty((M,), dtype=torch.float32, device=x.device)
+    check(lib().mq_act_quant_i8_dynamic(_ptr(x2), _ld(x2), _ptr(q), _ptr(srow), M, C, n_out,
+                                        float(clip_ratio), _stream()), "mq_act_quant_i8_dynamic")
+    return q, srow
+
+
+def hadamard(x, had_k=1, hadk=None, n=None, scales=None, modality=None, want_codes=False,
+             want_f16=True, split=False, fp32_had=False, want_row_scales=True):
+    """mq_hadamard_quant_i8.  Returns dict(y=fp16 [M,n] | None, q=int8 [M,n] | None, s_row, x0)."""
+    _need_cuda(x, hadk, scales, modality)
+    assert x.dtype == torch.float16
+    x2 = _as_rows(x)
+    M, C = x2.shape
+    n = C if n is None else n
+    dev = x.device
+    y = torch.empty((M, n), dtype=torch.float16, device=dev) if want_f16 else None
+    q = torch.empty((M, n), dtype=torch.int8, device=dev) if want_codes else None
+    srow = torch.empty((M,), dtype=torch.float32, device=dev) if (want_codes and want_row_scales) else None
+    x0 = torch.empty((M,), dtype=torch.float16, device=dev) if split else None
+    flags = (MQ_FLAG_SPLIT if split else 0) | (MQ_FLAG_FP32_HAD if fp32_had else 0)
+    if hadk is not None:
+        assert hadk.dtype == torch.float16 and hadk.is_contiguous() and hadk.shape == (had_k, had_k)
+    check(lib().mq_hadamard_quant_i8(_ptr(x2), _ld(x2), _ptr(q), _ptr(y), _ptr(srow), _ptr(x0),
+                                     _ptr(modality), _ptr(scales), _ptr(hadk), had_k, M, C, n, flags,
+                                     _stream()), "mq_hadamard_quant_i8")
+    return {"y": y, "q": q, "s_row": srow, "x0": x0}
+
+
+def observer_minmax(x, state, per_channel=False):
+    """mq_observer_minmax: merge x's min/max into `state` (fp32 [2] or [2*C], zero-initialised)."""
+    _need_cuda(x, state)
+    assert x.dtype == torch.float16 and state.dtype == torch.float32
+    x2 = _as_rows(x)
+    M, C = x2.shape
+    assert state.numel() == (2 * C if per_channel else 2)
+    check(lib().mq_observer_minmax(_ptr(x2), _ld(x2), M, C, 1 if per_channel else 0, _ptr(state),
+                                   _stream()), "mq_observer_minmax")
+    return state
+
+
+_pct_ws = {}
+
+
+def observer_percentile(x, alpha=0.99999):
+    """mq_observer_percentile -> fp32 [2] = {quantile(1-alpha), quantile(alpha)}."""
+    _need_cuda(x)
+    assert x.dtype == torch.float16
+    x2 = _as_rows(x)
+    M, C = x2.shape
+    nbytes = lib().mq_observer_percentile_workspace()
+    key = (x.device, torch.cuda.current_stream().cuda_stream)
+    ws = _pct_ws.get(key)
+    if ws is None:
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+        _pct_ws[key] = ws
+    out = torch.empty((2,), dtype=torch.float32, device=x.device)
+    check(lib().mq_observer_percentile(_ptr(x2), _ld(x2), M, C, float(alpha), _ptr(out), _ptr(ws),
+                                       nbytes, _stream()), "mq_observer_percentile")
+    return out
+
+
+def weight_quant_rtn(W, bits=4, scales=None):
+    """mq_weight_quant_rtn.  W: [N, K] fp16.  Returns (codes int8 [N,K], s_w fp32 [N])."""
+    _need_cuda(W, scales)
+    assert W.dtype == torch.float16 and W.dim() == 2
+    W = W.contiguous()
+    N, K = W.shape
+    codes = torch.empty((N, K), dtype=torch.int8, device=W.device)
+    s_w = torch.empty((N,), dtype=torch.float32, device=W.device)
+    if scales is not None:
+        scales = scales.detach().to(torch.float32).reshape(-1).contiguous()
+        assert scales.numel() == N
+    check(lib().mq_weight_quant_rtn(_ptr(W), W.stride(0), _ptr(codes), _ptr(s_w), _ptr(scales), N, K,
+                                    bits, _stream()), "mq_weight_quant_rtn")
+    return codes, s_w
+
+
+def pack_w4(codes, zero_col0=False):
+    _need_cuda(codes)
+    assert codes.dtype == torch.int8 and codes.dim() == 2
+    codes = codes.contiguous()
+    N, K = codes.shape
+    nbytes = lib().mq_w4_packed_bytes(N, K)
+    if nbytes == 0:
+        raise _lib.MQuantLibraryError(f"pack_w4: K={K} must be a positive multiple of 128")
+    w4 = torch.empty((nbytes,), dtype=torch.uint8, device=codes.device)
+    check(lib().mq_pack_w4(_ptr(codes), codes.stride(0), _ptr(w4), N, K, MQ_FLAG_SPLIT if zero_col0 else 0,
+                           _stream()), "mq_pack_w4")
+    return w4
+
+
+def repack_w4_from_ref(ref_packed, N, K):
+    _need_cuda(ref_packed)
+    assert ref_packed.dtype == torch.uint8 and ref_packed.shape == (N, K // 2)
+    ref_packed = ref_packed.contiguous()
+    nbytes = lib().mq_w4_packed_bytes(N, K)
+    w4 = torch.empty((nbytes,), dtype=torch.uint8, device=ref_packed.device)
+    check(lib().mq_repack_w4_from_ref(_ptr(ref_packed), _ptr(w4), N, K, _stream()), "mq_repack_w4_from_ref")
+    return w4
+
+
+def unpack_w4(w4, N, K):
+    _need_cuda(w4)
+    codes = torch.empty((N, K), dtype=torch.int8, device=w4.device)
+    check(lib().mq_unpack_w4(_ptr(w4), _ptr(codes), K, N, K, _stream()), "mq_unpack_w4")
+    return codes
+
+
+def w4a8_gemm(q, w4, s_a, s_w, N, bias=None, x0=None, w0=None, out=None, simt=False):
+    """mq_w4a8_gemm.  q: int8 [M, K]; s_a: fp32 [M] (per row) or [1]; s_w fp32 [N]."""
+    _need_cuda(q, w4, s_a, s_w, bias, x0, w0)
+    assert q.dtype == torch.int8 and q.dim() == 2 and q.stride(1) == 1
+    M, K = q.shape
+    if s_a.numel() not in (1, M):
+        raise _lib.MQuantLibraryError("w4a8_gemm: s_a must have 1 or M elements")
+    per_row = int(s_a.numel() == M)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float16, device=q.device)
+    fn = lib().mq_w4a8_gemm_simt if simt else lib().mq_w4a8_gemm
+    check(fn(_ptr(q), q.stride(0) if M > 1 else max(K, q.stride(0)), _ptr(w4), _ptr(s_a), per_row, _ptr(s_w),
+             _ptr(bias), _ptr(x0), _ptr(w0), _ptr(out), out.stride(0) if M > 1 else max(N, out.stride(0)),
+             M, N, K, _stream()), "mq_w4a8_gemm")
+    return out

@@ -1,0 +1,650 @@
+"""Quantized-linear path: API mirror of fake_quant/quant_utils.py:1-720 on B200 kernels.
+
+Same names, attributes and call protocol as the reference so that exam/quant_*.py and
+fake_quant/gptq/* run on top unchanged:
+
+  ActQuantizer      quant_utils.py:97-268     configure / forward / find_params / quantize / free
+  ActQuantWrapper   quant_utils.py:271-391    == QuantLinear; .module .weight .bias .quantizer
+                                              .out_quantizer .had_K .K .online_full_had
+                                              .online_partial_had .had_dim .fp32_had .split .L1 .L2
+  WeightQuantizer   quant_utils.py:415-524    configure / find_params / quantize / enabled / ready
+  add_actquant, find_qlayers, *_add_act_qaunt, model_open_calibrate, ...   quant_utils.py:543-720
+
+What is new (additive):
+  * the wrapper has a REAL integer path: ``freeze()`` packs the (already fake-quantised) weight
+    into INT4 and from then on ``forward`` = [online Hadamard +] static INT8 quantisation (one
+    fused kernel) -> tcgen05 W4A8 GEMM with the scale/bias/rank-1 epilogue.  Before ``freeze()``
+    the wrapper computes what the reference computes (fp16 fake-quant activations into a torch
+    Linear) so calibration and GPTQ see the same tensors.
+  * MSQ: ``ActQuantizer.configure(..., msq=True)`` keeps separate text / visual statistics and
+    scales; the per-token flag comes from ``mquant_b200.msq.modality_context``.
+There is no CPU execution path: forward on CPU tensors raises.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import hadamard_utils, msq, ops
+from .bit_type import BIT_TYPE_DICT
+from .observer import build_observer
+from .quantizer import build_quantizer
+
+
+def get_minq_maxq(bits, sym):
+    if sym:
+        maxq = torch.tensor(2 ** (bits - 1) - 1)
+        minq = -maxq - 1
+    else:
+        maxq = torch.tensor(2 ** bits - 1)
+        minq = 0
+    return minq, maxq
+
+
+# ---- integer-code helpers (reference :27-94) -------------------------------------------------
+
+def asym_quant(x, scale, zero, maxq):
+    scale = scale.to(x.device)
+    zero = zero.to(x.device)
+    q = torch.clamp(torch.round(x / scale) + zero, 0, maxq)
+    return q, scale, zero
+
+
+def asym_dequant(q, scale, zero):
+    return scale * (q - zero)
+
+
+def asym_quant_dequant(x, scale, zero, maxq):
+    return asym_dequant(*asym_quant(x, scale, zero, maxq))
+
+
+def sym_quant(x, scale, maxq):
+    scale = scale.to(x.device)
+    q = torch.clamp(torch.round(x / scale), -(maxq + 1), maxq)
+    return q, scale
+
+
+def sym_dequant(q, scale):
+    return scale * q
+
+
+def sym_quant_dequant(x, scale, maxq):
+    return sym_dequant(*sym_quant(x, scale, maxq))
+
+
+def two_compl(x, bits: int):
+    return torch.where(x < 0, 2 ** bits + x, x)
+
+
+def pack_i4(q):
+    """Interchange format of the reference (:61-68): even index -> low nibble."""
+    assert torch.is_signed(q), "The tensor to be packed should be signed int"
+    assert torch.all(torch.logical_and(q >= -8, q <= 7))
+    u = two_compl(q.to(dtype=torch.int8), 4).to(torch.uint8)
+    return u[:, 0::2] | (u[:, 1::2] << 4)
+
+
+def unpack_i4(x: torch.Tensor):
+    assert x.dtype == torch.uint8, "The tensor to be unpacked should be stored in uint8"
+    lo = (x & 0x0F).to(torch.int8)
+    lo = torch.where(lo >= 8, lo - 16, lo)
+    hi = ((x & 0xF0) >> 4).to(torch.int8)
+    hi = torch.where(hi >= 8, hi - 16, hi)
+    return torch.stack((lo, hi), dim=-1).reshape(*x.shape[:-1], x.shape[-1] * 2).to(torch.int32)
+
+
+# ---- activation quantizer ---------------------------------------------------------------------
+
+class ActQuantizer(torch.nn.Module):
+    """Reference quant_utils.py:97-268."""
+
+    def __init__(self, act_per_tensor=False):
+        super().__init__()
+        self.register_buffer("maxq", torch.tensor(0))
+        self.register_buffer("scale", torch.zeros(1))
+        self.register_buffer("zero", torch.zeros(1))
+        self.bits = 16
+        self.act_per_tensor = act_per_tensor
+        self.static = False
+        self.msq = False
+        self.sym = True
+
+    def free(self):
+        self.zero = None
+        self.scale = None
+        self._dyn = None
+
+    def configure(self, bits, groupsize=-1, sym=False, clip_ratio=1.0, act_per_tensor=False, static=False,
+                  observer_type="minmax", calibration_mode="layer_wise", msq=False):
+        _, self.maxq = get_minq_maxq(bits, sym)
+        self.bits = bits
+        self.groupsize = groupsize
+        self.sym = sym
+        self.clip_ratio = clip_ratio
+        self.act_per_tensor = act_per_tensor
+        assert 0 < self.clip_ratio <= 1, "Clip ratio should be in (0, 1]"
+        self.static = static
+        self.msq = bool(msq) and static
+        if self.static:
+            bit_type_a = BIT_TYPE_DICT[f"int{bits}"]  # KeyError for unsupported widths, as the reference
+            self.observer = build_observer(observer_type, "activation", bit_type_a, calibration_mode)
+            self.quantizer = build_quantizer("uniform", bit_type_a, self.observer, "activation")
+            self.observer_visual = (build_observer(observer_type, "activation", bit_type_a, calibration_mode)
+                                    if self.msq else None)
+            self.calibrate = False
+            self.last_calibrate = False
+            self.quant = False
+
+    # -- static path ---------------------------------------------------------------------------
+    def _modality(self, x):
+        if not self.msq:
+            return None
+        ntok = x.numel() // x.shape[-1]
+        return msq.current_modality(ntok, x.device)
+
+    def _observe(self, x):
+        mod = self._modality(x)
+        if mod is None:
+            self.observer.update(x)
+            return
+        x2 = x.reshape(-1, x.shape[-1])
+        vis = mod.bool()
+        if bool((~vis).any()):
+            self.observer.update(x2[~vis])
+        if bool(vis.any()):
+            self.observer_visual.update(x2[vis])
+
+    def update_quantization_params(self):
+        has_t = self.observer.max_val is not None
+        has_v = self.msq and self.observer_visual.max_val is not None
+        if has_t:
+            self.quantizer.update_quantization_params()
+        if has_v:
+            sv, _ = self.observer_visual.get_quantization_params()
+            if has_t:
+                self.quantizer.scale_visual = sv
+                self.quantizer._dev_scales = None
+            else:  # only visual tokens were ever seen
+                self.quantizer.set_scales(sv, sv)
+
+    def forward(self, x):
+        if self.static:
+            if self.calibrate:
+                self._observe(x)
+                if self.last_calibrate:
+                    self.update_quantization_params()
+                return x
+            elif self.quant:
+                return self.quantizer(x, self._modality(x))
+            return x
+        if self.bits == 16:
+            return x
+        if not (self.sym and self.bits == 8 and self.groupsize <= 0 and not self.act_per_tensor):
+            raise NotImplementedError("dynamic activation quantisation: only per-token symmetric INT8 "
+                                      "has a kernel (the MQuant recipes use static INT8)")
+        q, s = ops.act_quant_i8_dynamic(x, self.clip_ratio)
+        return (q.float() * s[:, None]).to(x.dtype).reshape(x.shape)
+
+    def quantize(self, x):
+        """Integer codes and scales (reference :136-140)."""
+        if self.static:
+            return self.quantizer.quant(x, modality=self._modality(x)), self.quantizer.scale
+        q, s = ops.act_quant_i8_dynamic(x, self.clip_ratio)
+        return q.reshape(x.shape), s.reshape(*x.shape[:-1], 1)
+
+    def find_params(self, x):
+        """Dynamic per-token scales (reference :205-268); kept for API compatibility: the codes
+        and scales are produced together by one kernel in forward()/quantize()."""
+        if self.bits == 16:
+            return
+        _, s = ops.act_quant_i8_dynamic(x, self.clip_ratio)
+        self.scale = s.reshape(*x.shape[:-1], 1)
+        self.zero = torch.zeros_like(self.scale)
+
+
+# ---- the wrapper ------------------------------------------------------------------------------
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class ActQuantWrapper(torch.nn.Module):
+    """Reference quant_utils.py:271-391, plus the real-integer path (see module docstring)."""
+
+    def __init__(self, module, act_per_tensor=False):
+        super().__init__()
+        assert isinstance(module, (torch.nn.Linear, torch.nn.Conv2d, torch.nn.Conv3d))
+        self.module = module
+        self.weight = module.weight
+        self.bias = module.bias
+        self.quantizer = ActQuantizer(act_per_tensor)
+        self.out_quantizer = ActQuantizer(act_per_tensor)
+        self.register_buffer("had_K", torch.tensor(0))
+        self._buffers["had_K"] = None
+        self.K = 1
+        self.online_full_had = False
+        self.online_partial_had = False
+        self.had_dim = 0
+        self.fp32_had = False
+        self.split = False
+        # new
+        self.pad_to = None       # fold utils.revise_down_input into the fused kernel
+        self.real_quant = False  # set by freeze()
+        self._packed = None
+
+    def extra_repr(self) -> str:
+        s = f"Input Quantizer Bits: {self.quantizer.bits}"
+        if self.quantizer.bits < 16:
+            s += " (Symmetric" if self.quantizer.sym else " (Asymmetric"
+            s += " Static Per-Tensor)" if self.quantizer.static else " Per-Token)"
+        s += f"\nOutput Quantizer Bits: {self.out_quantizer.bits}"
+        if self.real_quant:
+            s += "\nW4A8 real-integer path (tcgen05)"
+        return s
+
+    def split_weights(self):
+        """RMS split (reference :316-328): channel 0 gets its own fp Linear."""
+        m = self.module
+        self.L1 = torch.nn.Linear(1, m.out_features, bias=False).to(m.weight.device)
+        self.L2 = torch.nn.Linear(m.in_features - 1, m.out_features, bias=m.bias is not None).to(m.weight.device)
+        self.L1.weight.data = m.weight.data[:, 0:1]
+        self.L2.weight.data = m.weight.data[:, 1:]
+        if m.bias is not None:
+            self.L2.bias.data = m.bias.data
+
+    # -- real-integer path -----------------------------------------------------------------------
+    @torch.no_grad()
+    def freeze(self, w_scale=None, w_bits=4):
+        """Pack the current (fake-quantised, fp16) weight into INT4 for the W4A8 GEMM.
+
+        w_scale: the per-output-channel scale the weight was quantised with
+        (``WeightQuantizer.scale``, shape [N,1]); codes = round(W / scale) are then recovered
+        exactly (SURVEY.md 8(c) self-check).  If omitted the weight is re-quantised RTN
+        (quant_utils.py:446-466) -- identical codes when the weight already sits on a 4-bit grid.
+        """
+        if not isinstance(self.module, torch.nn.Linear):
+            raise NotImplementedError("freeze(): only Linear layers have an integer path")
+        if not (self.quantizer.static and self.quantizer.bits == 8):
+            raise RuntimeError("freeze(): configure the activation quantizer as static INT8 first")
+        if w_bits != 4:
+            raise NotImplementedError("freeze(): the GEMM takes INT4 weights")
+        if self.split:
+            W = torch.cat([self.L1.weight.data.to(torch.float16), self.L2.weight.data.to(torch.float16)], 1)
+            bias = self.L2.bias
+        else:
+            W = self.module.weight.data.to(torch.float16)
+            bias = self.module.bias
+        if not W.is_cuda:
+            raise ops._lib.MQuantLibraryError("freeze() needs the weights on a CUDA device")
+        N, K = W.shape
+        if w_scale is not None:
+            w_scale = w_scale.to(W.device)
+        if self.split:
+            body = W.clone()
+            body[:, 0] = 0  # channel 0 is the fp rank-1 term; it must not steer the RTN scale
+            codes, s_w = ops.weight_quant_rtn(body, w_bits, w_scale)
+            w0 = W[:, 0].contiguous()
+        else:
+            codes, s_w = ops.weight_quant_rtn(W, w_bits, w_scale)
+            w0 = None
+        Kp = _round_up(max(K, self.pad_to or 0), 128)
+        if Kp != K:
+            codes = torch.nn.functional.pad(codes, (0, Kp - K))
+        self._packed = {
+            "w4": ops.pack_w4(codes, zero_col0=self.split),
+            "s_w": s_w, "w0": w0, "N": N, "K": K, "Kp": Kp,
+            "bias": None if bias is None else bias.data.to(torch.float16).contiguous(),
+        }
+        self.real_quant = True
+        return self
+
+    def _forward_real(self, x):
+        pk = self._packed
+        qz = self.quantizer.quantizer
+        x2 = x.reshape(-1, x.shape[-1])
+        M = x2.shape[0]
+        scales = qz.device_scales(x.device)
+        modality = self.quantizer._modality(x) if qz.scale_visual is not None else None
+        if self.online_full_had:
+            n = self.pad_to or x2.shape[-1]
+            hk = hadamard_utils.hadK_device(self.K, x.device) if self.K > 1 else None
+            r = ops.hadamard(x2, had_k=self.K, hadk=hk, n=n, scales=scales, modality=modality,
+                             want_codes=True, want_f16=False, split=self.split, fp32_had=self.fp32_had,
+                             want_row_scales=modality is not None)
+            q, srow, x0 = r["q"], r["s_row"], r["x0"]
+            if q.shape[1] != pk["Kp"]:
+                q = torch.nn.functional.pad(q, (0, pk["Kp"] - q.shape[1]))
+        else:
+            q, srow, x0 = ops.act_quant_i8(x2, scales, modality, n_out=pk["Kp"], split=self.split,
+                                           want_row_scales=modality is not None)
+        s_a = srow if modality is not None else scales[0:1]
+        out = ops.w4a8_gemm(q, pk["w4"], s_a, pk["s_w"], pk["N"], bias=pk["bias"], x0=x0, w0=pk["w0"])
+        return out.reshape(*x.shape[:-1], pk["N"])
+
+    # -- reference-equivalent (fake-quant) path ---------------------------------------------------
+    def _rotate(self, x):
+        if self.online_full_had:
+            n = self.pad_to or x.shape[-1]
+            hk = hadamard_utils.hadK_device(self.K, x.device) if self.K > 1 else None
+            y = ops.hadamard(x, had_k=self.K, hadk=hk, n=n, fp32_had=self.fp32_had)["y"]
+            return y.reshape(*x.shape[:-1], n)
+        if self.online_partial_had:
+            raise NotImplementedError("online_partial_had is never enabled by the reference drivers")
+        if self.pad_to and self.pad_to > x.shape[-1]:
+            return torch.nn.functional.pad(x, (0, self.pad_to - x.shape[-1]))
+        return x
+
+    def forward(self, x):
+        x_dtype = x.dtype
+        q = self.quantizer
+        if (self.real_quant and q.static and q.quant and not q.calibrate
+                and x.dtype == torch.float16 and self.out_quantizer.bits >= 16):
+            return self._forward_real(x)
+
+        x = self._rotate(x)
+        if self.split:
+            if q.static:
+                if q.calibrate:
+                    obs = x.clone()
+                    obs[..., 0] = 0  # the reference observes x[..., 1:]; 0 is already folded in
+                    q(obs)
+                elif q.quant:
+                    x0 = x[..., 0].clone()
+                    x = q(x)
+                    x[..., 0] = x0
+            elif q.bits < 16:
+                x0 = x[..., 0].clone()
+                x = q(x.clone().index_fill_(-1, torch.zeros(1, dtype=torch.long, device=x.device), 0))
+                x[..., 0] = x0
+            x1 = self.L1.float()(x[..., 0:1].float())
+            x2 = self.L2.float()(x[..., 1:].float())
+            x = (x1 + x2).to(x_dtype)
+        else:
+            if q.static or q.bits < 16:
+                x = q(x)
+            x = self.module(x).to(x_dtype)
+        if self.out_quantizer.bits < 16:
+            x = self.out_quantizer(x).to(x_dtype)
+        return x
+
+
+QuantLinear = ActQuantWrapper  # the north-star's name for the drop-in unit
+
+
+class ActRotateWrapper(torch.nn.Module):
+    """Reference quant_utils.py:394-412 (dense rotation of two inputs; offline experiments only)."""
+
+    def __init__(self, module, QMatrix):
+        super().__init__()
+        self.module = module
+        self.register_buffer("q_matrix", QMatrix)
+        self.fp32_had = False
+
+    def forward(self, x, y):
+        x_dtype = x.dtype
+        if self.fp32_had:
+            x = (x.float() @ self.q_matrix).to(x_dtype)
+            y.copy_((y.float() @ self.q_matrix).to(y.dtype))
+        else:
+            x = x @ self.q_matrix
+            y.copy_(y @ self.q_matrix.to(y.dtype))
+        return self.module(x, y).to(x_dtype)
+
+
+# ---- weight quantizer ---------------------------------------------------------------------------
+
+class WeightQuantizer(torch.nn.Module):
+    """Reference quant_utils.py:415-524 ("From GPTQ Repo").  Statistics are torch reductions over
+    an [N, K] matrix (offline, once per layer); the per-channel symmetric RTN that the W4A8
+    recipes use also exists as a kernel (ops.weight_quant_rtn) which ``freeze`` calls."""
+
+    def __init__(self, shape=1):
+        super().__init__()
+        self.register_buffer("maxq", torch.tensor(0))
+        self.register_buffer("scale", torch.zeros(shape))
+        self.register_buffer("zero", torch.zeros(shape))
+
+    def configure(self, bits, perchannel=False, sym=True, mse=False, norm=2.4, grid=100, maxshrink=0.8):
+        self.bits = bits
+        self.perchannel = perchannel
+        self.sym = sym
+        self.mse = mse
+        self.norm = norm
+        self.grid = grid
+        self.maxshrink = maxshrink
+        self.maxq = torch.tensor(2 ** (bits - 1) - 1) if sym else torch.tensor(2 ** bits - 1)
+
+    def find_params(self, x):
+        if self.bits == 16:
+            return
+        dev = x.device
+        self.maxq = self.maxq.to(dev)
+        shape = x.shape
+        x = x.flatten(1) if self.perchannel else x.flatten().unsqueeze(0)
+        zeros = torch.zeros(x.shape[0], device=dev)
+        xmin = torch.minimum(x.min(1)[0], zeros)
+        xmax = torch.maximum(x.max(1)[0], zeros)
+        if self.sym:
+            xmax = torch.maximum(torch.abs(xmin), xmax).clamp(min=1e-5)
+            self.scale = xmax / self.maxq
+            self.zero = torch.zeros_like(self.scale)
+        else:
+            both0 = (xmin == 0) & (xmax == 0)
+            xmin[both0] = -1
+            xmax[both0] = +1
+            self.scale = (xmax - xmin).clamp(min=1e-5) / self.maxq
+            self.zero = torch.round(-xmin / self.scale)
+        if self.mse:
+            best = torch.full([x.shape[0]], float("inf"), device=dev)
+            for i in range(int(self.maxshrink * self.grid)):
+                p = 1 - i / self.grid
+                xmin1, xmax1 = p * xmin, p * xmax
+                if self.sym:
+                    scale1 = xmax1 / self.maxq
+                    zero1 = torch.zeros_like(scale1)
+                    q = sym_quant_dequant(x, scale1.unsqueeze(1), self.maxq)
+                else:
+                    scale1 = (xmax1 - xmin1) / self.maxq
+                    zero1 = torch.round(-xmin1 / scale1)
+                    q = asym_quant_dequant(x, scale1.unsqueeze(1), zero1.unsqueeze(1), self.maxq)
+                q -= x
+                q.abs_()
+                q.pow_(self.norm)
+                err = torch.sum(q, 1)
+                better = err < best
+                if torch.any(better):
+                    best[better] = err[better]
+                    self.scale[better] = scale1[better]
+                    self.zero[better] = zero1[better]
+        if not self.perchannel:
+            self.scale = self.scale.repeat(shape[0])
+            self.zero = self.zero.repeat(shape[0])
+        bshape = [-1] + [1] * (len(shape) - 1)
+        self.scale = self.scale.reshape(bshape)
+        self.zero = self.zero.reshape(bshape)
+
+    def quantize(self, x):
+        x_dtype = x.dtype
+        if self.ready() and self.bits < 16:
+            if self.sym:
+                return sym_quant_dequant(x, self.scale, self.maxq).to(x_dtype)
+            return asym_quant_dequant(x, self.scale, self.zero, self.maxq).to(x_dtype)
+        return x
+
+    def enabled(self):
+        return self.maxq > 0
+
+    def ready(self):
+        return torch.all(self.scale != 0)
+
+
+# ---- module-tree surgery and flag broadcast (reference :543-720) ---------------------------------
+
+def add_actquant(module, act_per_tensor=False, name="", layers=[torch.nn.Linear]):
+    """Wrap every exact-type match (reference :626-662; `type(tmp) in layers`, Sequential and
+    ModuleList children included)."""
+    if isinstance(module, ActQuantWrapper):
+        return
+    for attr in dir(module):
+        tmp = getattr(module, attr)
+        if type(tmp) in layers:
+            setattr(module, attr, ActQuantWrapper(tmp, act_per_tensor))
+        if type(tmp) == torch.nn.Sequential:
+            replaced = OrderedDict()
+            for cname, child in tmp.named_children():
+                replaced[cname] = ActQuantWrapper(child, act_per_tensor) if type(child) in layers else child
+            setattr(module, attr, torch.nn.Sequential(replaced))
+        if type(tmp) == torch.nn.ModuleList:
+            replaced = [ActQuantWrapper(c, act_per_tensor) if type(c) in layers else c for c in tmp.children()]
+            setattr(module, attr, torch.nn.ModuleList(replaced))
+    for name1, child in module.named_children():
+        add_actquant(child, act_per_tensor, name + "." + name1 if name != "" else name1, [torch.nn.Linear])
+
+
+def add_actquant_for_mlp1(module, act_per_tensor=False, name="", layers=[torch.nn.Linear]):
+    module.mlp1[1] = ActQuantWrapper(module.mlp1[1], act_per_tensor)
+    module.mlp1[3] = ActQuantWrapper(module.mlp1[3], act_per_tensor)
+
+
+def find_qlayers(module, layers=[torch.nn.Linear, ActQuantWrapper], name=""):
+    if type(module) in layers:
+        return {name: module}
+    res = {}
+    for name1, child in module.named_children():
+        res.update(find_qlayers(child, layers=layers, name=name + "." + name1 if name != "" else name1))
+    return res
+
+
+def internvl_add_act_qaunt(model, args):
+    if args.quant_llm:
+        add_actquant(model.model.language_model.model, args.act_per_tensor)
+    if args.quant_visual_clip:
+        emb = model.model.vision_model.embeddings
+        emb.patch_embedding = ActQuantWrapper(emb.patch_embedding, args.act_per_tensor)
+        add_actquant(model.model.vision_model.encoder, args.act_per_tensor)
+    if args.quant_cross_attention:
+        add_actquant_for_mlp1(model.model, args.act_per_tensor)
+
+
+def qwen2vl_add_act_qaunt(model, args):
+    if args.quant_llm:
+        add_actquant(model.model.model, args.act_per_tensor)
+    if args.quant_visual_clip:
+        pe = model.model.visual.patch_embed
+        pe.proj = ActQuantWrapper(pe.proj, args.act_per_tensor)
+        add_actquant(model.model.visual.blocks, args.act_per_tensor)
+    if args.quant_cross_attention:
+        add_actquant(model.model.visual.merger, args.act_per_tensor)
+
+
+def qwenvl_add_act_qaunt(model, args):
+    if args.quant_llm:
+        add_actquant(model.transformer.h, args.act_per_tensor)
+    if args.quant_visual_clip:
+        vis = model.transformer.visual
+        vis.conv1 = ActQuantWrapper(vis.conv1, args.act_per_tensor)
+        add_actquant(vis.transformer, args.act_per_tensor)
+    if args.quant_cross_attention:
+        add_actquant(model.transformer.visual.attn_pool, args.act_per_tensor)
+        model.transformer.visual.proj_fc = ActQuantWrapper(model.transformer.visual.proj_fc, args.act_per_tensor)
+
+
+def minicpmv_add_act_qaunt(model, args):
+    if args.quant_llm:
+        add_actquant(model.llm.model.layers, args.act_per_tensor)
+    if args.quant_visual_clip:
+        emb = model.vpm.embeddings
+        emb.patch_embedding = ActQuantWrapper(emb.patch_embedding, args.act_per_tensor)
+        add_actquant(model.vpm.encoder, args.act_per_tensor)
+    if args.quant_cross_attention:
+        add_actquant(model.resampler, args.act_per_tensor)
+
+
+@torch.no_grad()
+def fuse_internvl(model):
+    """Fold InternViT layer-scale vectors into the following Linear (reference :527-541)."""
+    for layer in model.model.vision_model.encoder.layers:
+        layer.attn.proj.weight.data *= layer.ls1.data.view(-1, 1)
+        layer.mlp.fc2.weight.data *= layer.ls2.data.view(-1, 1)
+        if hasattr(layer.attn.proj, "bias"):
+            layer.attn.proj.bias.data *= layer.ls1.data
+        if hasattr(layer.mlp.fc2, "bias"):
+            layer.mlp.fc2.bias.data *= layer.ls2.data
+        layer.ls1[:] = 1
+        layer.ls2[:] = 1
+
+
+def _set_flag(model, args, flag, value):
+    skip = getattr(args, "skip_names", None) or []
+    for name, layer in find_qlayers(model, layers=[ActQuantWrapper]).items():
+        if any(p in name for p in skip):
+            continue
+        setattr(layer.quantizer, flag, value)
+    return model
+
+
+def model_open_calibrate(model, args):
+    return _set_flag(model, args, "calibrate", True)
+
+
+def model_open_last_calibrate(model, args):
+    return _set_flag(model, args, "last_calibrate", True)
+
+
+def model_close_calibrate(model, args):
+    return _set_flag(model, args, "calibrate", False)
+
+
+def model_quant(model, args):
+    return _set_flag(model, args, "quant", True)
+
+
+def model_no_quant(model, args):
+    return _set_flag(model, args, "quant", False)
+
+
+@torch.no_grad()
+def model_freeze(model, args=None, weight_quantizers=None):
+    """New: switch every calibrated Linear wrapper to the real W4A8 path.  ``weight_quantizers`` is
+    the dict the reference's gptq entry points return (name -> WeightQuantizer); names ending in
+    ".module" / ".L2" are matched to their wrapper."""
+    skip = getattr(args, "skip_names", None) or []
+    scales = {}
+    for k, wq in (weight_quantizers or {}).items():
+        base = k.rsplit(".", 1)[0] if k.endswith((".module", ".L2")) else k
+        scales[base] = wq.scale
+    n = 0
+    for name, layer in find_qlayers(model, layers=[ActQuantWrapper]).items():
+        if any(p in name for p in skip) or not isinstance(layer.module, torch.nn.Linear):
+            continue
+        q = layer.quantizer
+        if not (q.static and q.bits == 8 and q.quantizer.scale is not None):
+            continue
+        ws = None
+        for key, s in scales.items():
+            if key.endswith(name) or name.endswith(key):
+                ws = s
+                break
+        layer.freeze(ws)
+        n += 1
+    return n
+
+
+# ---- calibration protocol (reference calib_vqa_plus, :1079-1102, with synthetic batches) ----------
+
+@torch.no_grad()
+def calibrate_static(model, args, batches, forward=None):
+    """N forward passes with observers on, parameters set on the last one, then quant on.
+    ``batches``: iterable of model inputs; ``forward(model, batch)`` defaults to ``model(batch)``."""
+    forward = forward or (lambda m, b: m(b))
+    batches = list(batches)
+    model_open_calibrate(model, args)
+    for i, b in enumerate(batches):
+        if i == len(batches) - 1:
+            model_open_last_calibrate(model, args)
+        forward(model, b)
+    model_close_calibrate(model, args)
+    model_quant(model, args)
+    return model

@@ -1,0 +1,69 @@
+"""UniformQuantizer on the GPU (mirror of fake_quant/quantizer/uniform.py:8-43 driven by
+BaseQuantizer.forward, base.py:44-50).
+
+``scale`` / ``zero_point`` keep the reference's types (scale in the activation dtype, int64 zero
+point).  MSQ extension: ``scale_visual`` is a second per-tensor scale used for tokens whose
+modality flag is set; with ``scale_visual is None`` the quantizer is exactly the reference's.
+"""
+import torch
+
+from .. import ops
+from .base import BaseQuantizer
+
+
+class UniformQuantizer(BaseQuantizer):
+    def __init__(self, bit_type, observer, module_type):
+        super().__init__(bit_type, observer, module_type)
+        self.scale = None
+        self.zero_point = None
+        self.scale_visual = None
+        self._dev_scales = None  # fp32 [2] {text, visual} (layer_wise) or [C] (channel_wise)
+
+    def update_quantization_params(self, *args, **kwargs):
+        self.scale, self.zero_point = self.observer.get_quantization_params(*args, **kwargs)
+        self._dev_scales = None
+
+    def set_scales(self, scale, scale_visual=None):
+        """Install calibrated scales directly (checkpoint load / MSQ calibration)."""
+        self.scale = scale
+        self.scale_visual = scale_visual
+        self.zero_point = torch.zeros_like(scale, dtype=torch.int64)
+        self._dev_scales = None
+
+    @property
+    def per_channel(self):
+        return self.scale is not None and self.scale.dim() > 0 and self.scale.numel() > 1
+
+    def device_scales(self, device):
+        if self.scale is None:
+            raise RuntimeError("UniformQuantizer used before calibration (scale is None)")
+        if self._dev_scales is None or self._dev_scales.device != device:
+            if self.per_channel:
+                self._dev_scales = self.scale.detach().to(device=device, dtype=torch.float32).contiguous()
+            else:
+                self._dev_scales = ops.make_scales(self.scale, self.scale_visual, device)
+        return self._dev_scales
+
+    def _check_symmetric(self):
+        if not self.bit_type.signed:
+            raise NotImplementedError("unsigned activation types are unreachable from ActQuantizer.configure")
+
+    def quant(self, inputs, scale=None, zero_point=None, modality=None):
+        """INT8 codes (int8 tensor, same shape).  The reference returns them as fp32."""
+        self._check_symmetric()
+        if self.bit_type.bits != 8 or self.per_channel:
+            raise NotImplementedError("integer codes are produced for per-tensor INT8 only")
+        x = inputs if inputs.dtype == torch.float16 else inputs.to(torch.float16)
+        q, _, _ = ops.act_quant_i8(x, self.device_scales(x.device), modality, want_row_scales=False)
+        return q.reshape(inputs.shape)
+
+    def dequantize(self, inputs, scale=None, zero_point=None):
+        s = self.scale if scale is None else scale
+        return (inputs.float() * s.float())
+
+    def forward(self, inputs, modality=None):
+        self._check_symmetric()
+        if inputs.dtype != torch.float16:
+            raise NotImplementedError("mquant_b200 quantises fp16 activations (model.half())")
+        return ops.act_fake_quant(inputs, self.device_scales(inputs.device), modality,
+                                  bits=self.bit_type.bits, per_channel=self.per_channel)
