@@ -1,0 +1,71 @@
+"""world_size-2 gloo tests of the sharded-calibration merge (host logic; no GPU)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import mq_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mquant_b200 import dist as mqd
+
+    rng = np.random.default_rng(0)
+    samples = [(rng.standard_normal((int(rng.integers(4, 32)), 64)) * 3).astype(np.float16) for _ in range(11)]
+    mine = mqd.shard_indices(len(samples), rank, world)
+    # local statistics as the observer kernel would leave them: {min, max} / {min[C], max[C]}
+    states = []
+    for per_channel in (False, True):
+        ob = O.MinmaxObserver(8, "channel_wise" if per_channel else "layer_wise")
+        for i in mine:
+            ob.update(samples[i])
+        mn = np.asarray(ob.min_val, dtype=np.float32).reshape(-1)
+        mx = np.asarray(ob.max_val, dtype=np.float32).reshape(-1)
+        states.append(torch.from_numpy(np.concatenate([mn, mx])))
+    mqd.merge_observer_states(states)
+    ret[rank] = [s.numpy().copy() for s in states]
+    dist.destroy_process_group()
+
+
+def test_sharded_minmax_merge_is_bit_identical_to_sequential():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    rng = np.random.default_rng(0)
+    samples = [(rng.standard_normal((int(rng.integers(4, 32)), 64)) * 3).astype(np.float16) for _ in range(11)]
+    for k, per_channel in enumerate((False, True)):
+        ob = O.MinmaxObserver(8, "channel_wise" if per_channel else "layer_wise")
+        for s in samples:
+            ob.update(s)
+        want = np.concatenate([np.asarray(ob.min_val, np.float32).reshape(-1),
+                               np.asarray(ob.max_val, np.float32).reshape(-1)])
+        for r in range(world):
+            assert np.array_equal(ret[r][k], want)
+        # and the scales every rank derives are the sequential ones
+        half = want.size // 2
+        s_seq, _ = ob.get_quantization_params()
+        s_rank, _ = O.minmax_params(ret[0][k][:half].astype(np.float16), ret[0][k][half:].astype(np.float16))
+        assert np.array_equal(np.asarray(s_seq).reshape(-1).view(np.uint16), np.asarray(s_rank).reshape(-1).view(np.uint16))
+
+
+def test_shard_indices_cover_everything():
+    from mquant_b200 import dist as mqd
+
+    for world in (1, 2, 4, 8):
+        got = sorted(i for r in range(world) for i in mqd.shard_indices(256, r, world))
+        assert got == list(range(256))

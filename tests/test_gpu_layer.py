@@ -1,0 +1,123 @@
+"""Layer-level parity on the GPU: QuantLinear (= ActQuantWrapper) against the reference wrapper's
+frozen outputs (tests/golden/wrapper.npz) and against the integer oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def qu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import mquant_b200
+    from mquant_b200 import quant_utils
+
+    mquant_b200.lib()
+    return quant_utils
+
+
+def cos_maxabs(y, ref):
+    y = y.astype(np.float64).ravel()
+    ref = ref.astype(np.float64).ravel()
+    return float(y @ ref / np.sqrt((y @ y) * (ref @ ref))), float(np.abs(y - ref).max())
+
+
+def build_wrapper(qu, g, tag, K_in, N_out, had, split):
+    from mquant_b200 import hadamard_utils as hu
+
+    has_b = f"{tag}_b" in g.files
+    lin = torch.nn.Linear(K_in, N_out, bias=has_b).half().cuda()
+    lin.weight.data = torch.from_numpy(g[f"{tag}_W"]).cuda()
+    if has_b:
+        lin.bias.data = torch.from_numpy(g[f"{tag}_b"]).cuda()
+    w = qu.ActQuantWrapper(lin)
+    if had:
+        w.online_full_had = True
+        w.had_K, w.K = hu.get_hadK(K_in)
+    if split:
+        w.split = True
+        w.split_weights()
+    w.quantizer.configure(bits=8, sym=True, static=True, observer_type="minmax")
+    w.quantizer.quantizer.set_scales(torch.from_numpy(g[f"{tag}_act_scale"]).cuda())
+    w.quantizer.quant = True
+    return w
+
+
+CASES = [("plain", 256, 128, False, False), ("had256", 256, 64, True, False)]
+
+
+@pytest.mark.parametrize("tag,K_in,N_out,had,split", CASES)
+def test_wrapper_fake_and_real_paths(qu, golden, tag, K_in, N_out, had, split):
+    g = golden("wrapper")
+    w = build_wrapper(qu, g, tag, K_in, N_out, had, split)
+    x = torch.from_numpy(g[f"{tag}_x"]).cuda()
+    ref = g[f"{tag}_y"]
+    # (1) unfrozen: the reference's computation on our kernels (fp16 fake quant -> cuBLAS Linear)
+    y_fake = w(x.clone()).cpu().numpy()
+    cos, err = cos_maxabs(y_fake, ref)
+    assert cos > 0.99999 and err <= 2.0 ** -9 * np.abs(ref).max() + 1e-3, (cos, err)
+    # (2) frozen: real INT8 x INT4 path; tolerance of SURVEY.md 8(c)
+    w.freeze(torch.from_numpy(g[f"{tag}_wscale"]).cuda())
+    y_real = w(x.clone()).cpu().numpy()
+    cos, err = cos_maxabs(y_real, ref)
+    assert cos >= 0.9999 and err <= 2.0 ** -9 * np.abs(ref).max() * 4, (cos, err)
+    # (3) and bit-exact against the integer oracle on our own codes
+    x2 = g[f"{tag}_x"].reshape(-1, K_in)
+    s_a = np.float32(g[f"{tag}_act_scale"])
+    s_w = g[f"{tag}_wscale"].reshape(-1)
+    xr = x2
+    if had:
+        from mquant_b200 import ops
+        xr = ops.hadamard(torch.from_numpy(x2).cuda(), n=K_in)["y"].cpu().numpy()
+    ca = O.act_quant_codes(xr, s_a)
+    cw = np.rint(g[f"{tag}_W"].astype(np.float32) / s_w[:, None]).astype(np.int8)
+    b = g[f"{tag}_b"] if f"{tag}_b" in g.files else None
+    want = O.qlinear_int(ca, s_a, cw, s_w, b)
+    assert np.array_equal(y_real.reshape(want.shape).view(np.uint16), want.view(np.uint16))
+
+
+def test_qwenvl_mlp_down_proj_layer(qu):
+    """Qwen-VL down_proj shape: K = 11008 = 172 x 64 online Hadamard, split off/on, MSQ."""
+    from mquant_b200 import hadamard_utils as hu, msq, ops
+
+    torch.manual_seed(0)
+    K_in, N_out, M = 11008, 4096, 192
+    lin = torch.nn.Linear(K_in, N_out, bias=False).half().cuda()
+    hu.apply_exact_had_to_linear(lin, had_dim=-1, output=False)
+    x = (torch.randn(1, M, K_in, device="cuda") * 2).half()
+    y_fp = lin(hu.matmul_hadU_cuda(x, *hu.get_hadK(K_in)))
+    for split in (False, True):
+        w = qu.ActQuantWrapper(torch.nn.Linear(K_in, N_out, bias=False).half().cuda())
+        w.module.weight.data = lin.weight.data.clone()
+        w.online_full_had = True
+        w.had_K, w.K = hu.get_hadK(K_in)
+        if split:
+            w.split = True
+            w.split_weights()
+        # RTN W4 as the reference's qwenvl_llm_rtn does, through WeightQuantizer
+        tgt = w.L2 if split else w.module
+        wq = qu.WeightQuantizer()
+        wq.configure(4, perchannel=True, sym=True, mse=False)
+        wq.find_params(tgt.weight.data)
+        tgt.weight.data = wq.quantize(tgt.weight.data).to(torch.float16)
+        w.quantizer.configure(bits=8, sym=True, static=True, observer_type="minmax", msq=True)
+        mask = torch.zeros(M, dtype=torch.uint8, device="cuda")
+        mask[32:96] = 1
+        args = type("A", (), {"skip_names": []})()
+        with msq.modality_context(mask):
+            qu.calibrate_static(w, args, [x, x * 0.5], forward=lambda m, b: m(b.clone()))
+            y_fake = w(x.clone())
+            w.freeze(wq.scale)
+            y_real = w(x.clone())
+        sc = w.quantizer.quantizer
+        assert sc.scale is not None and sc.scale_visual is not None
+        for y in (y_fake, y_real):
+            c = torch.nn.functional.cosine_similarity(y.float().flatten(), y_fp.float().flatten(), dim=0)
+            assert c > 0.98, float(c)  # W4A8 vs fp16: quantisation noise only
+        cos, err = cos_maxabs(y_real.cpu().numpy(), y_fake.cpu().numpy())
+        assert cos >= 0.9999, (split, cos, err)
+        assert err <= 2.0 ** -9 * float(y_fake.abs().max()) * 4, (split, err)

@@ -1,0 +1,146 @@
+"""Per-kernel timings on one GPU (CUDA events, L2 flushed between iterations).
+
+python tools/microbench.py [--quick] [--json out.json]
+Prints achieved GB/s (HBM-bound kernels, algorithmic bytes of SURVEY.md 8(d)) or TOP/s (GEMM,
+2*M*N*K) next to the measured peaks of MEASURED_PEAKS.json."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    _flush.zero_()
+
+
+def timeit(fn, iters=10, warmup=3, flush=True):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2] * 1e-3, ts[0] * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    from mquant_b200 import hadamard_utils as hu, ops
+
+    hbm, bf16, src = peaks()
+    print(f"peaks ({src}): HBM {hbm:.0f} GB/s, bf16 {bf16:.0f} TFLOP/s; INT8 nominal 4500 TOP/s")
+    rows = []
+
+    def rec(name, shape, sec, best, bytes_=None, ops_=None):
+        r = {"kernel": name, "shape": shape, "ms": sec * 1e3, "ms_best": best * 1e3}
+        if bytes_:
+            r["GBps"] = bytes_ / sec / 1e9
+            r["frac_hbm"] = r["GBps"] / hbm
+        if ops_:
+            r["TOPs"] = ops_ / sec / 1e12
+            r["frac_int8_nominal"] = r["TOPs"] / 4500.0
+        rows.append(r)
+        print(json.dumps(r))
+
+    Ms = [4096] if a.quick else [1024, 4096, 16384]
+    scales = ops.make_scales(0.05, 0.11, "cuda")
+    want = lambda k: (not a.only) or k in a.only.split(",")
+
+    if want("int8ref"):
+        # library INT8 GEMM (cuBLASLt via torch._int_mm): the measured INT8 reference point
+        n = 8192
+        A = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda")
+        B = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda").t()
+        try:
+            sec, best = timeit(lambda: torch._int_mm(A, B), flush=False)
+            rec("cublaslt_int8_mm", f"{n}^3", sec, best, ops_=2 * n ** 3)
+        except Exception as e:  # noqa: BLE001
+            print("int8 library GEMM unavailable:", e)
+        A16 = torch.randn(n, n, dtype=torch.bfloat16, device="cuda")
+        B16 = torch.randn(n, n, dtype=torch.bfloat16, device="cuda")
+        sec, best = timeit(lambda: A16 @ B16, flush=False)
+        rec("cublas_bf16_mm", f"{n}^3", sec, best, ops_=2 * n ** 3)
+        del A, B, A16, B16
+
+    for M in Ms:
+        for C in (4096, 11008):
+            x = (torch.randn(M, C, device="cuda") * 3).half()
+            mod = (torch.rand(M, device="cuda") < 0.4).to(torch.uint8)
+            if want("quant"):
+                sec, best = timeit(lambda: ops.act_quant_i8(x, scales, mod))
+                rec("act_quant_i8_msq", f"{M}x{C}", sec, best, bytes_=3 * M * C + M)
+            if want("fake"):
+                sec, best = timeit(lambda: ops.act_fake_quant(x, scales, mod))
+                rec("act_fake_quant", f"{M}x{C}", sec, best, bytes_=4 * M * C + M)
+            if want("minmax"):
+                st = torch.zeros(2, dtype=torch.float32, device="cuda")
+                sec, best = timeit(lambda: ops.observer_minmax(x, st))
+                rec("observer_minmax", f"{M}x{C}", sec, best, bytes_=2 * M * C)
+                stc = torch.zeros(2 * C, dtype=torch.float32, device="cuda")
+                sec, best = timeit(lambda: ops.observer_minmax(x, stc, True))
+                rec("observer_minmax_cw", f"{M}x{C}", sec, best, bytes_=2 * M * C)
+            if want("pct") and M <= 4096:
+                sec, best = timeit(lambda: ops.observer_percentile(x))
+                rec("observer_percentile", f"{M}x{C}", sec, best, bytes_=4 * M * C)
+            if want("dyn"):
+                sec, best = timeit(lambda: ops.act_quant_i8_dynamic(x))
+                rec("act_quant_dynamic", f"{M}x{C}", sec, best, bytes_=3 * M * C)
+            if want("had"):
+                hk_, K_ = hu.get_hadK(C)
+                hk = hu.hadK_device(K_, "cuda") if K_ > 1 else None
+                sec, best = timeit(lambda: ops.hadamard(x, had_k=K_, hadk=hk, n=C, scales=scales, modality=mod,
+                                                        want_codes=True, want_f16=False))
+                rec(f"hadamard_quant_k{K_}", f"{M}x{C}", sec, best, bytes_=3 * M * C + M)
+            del x
+
+    if want("gemm"):
+        shapes = [(4096, 4096), (4096, 11008), (11008, 4096)]
+        for M in ([16, 4096] if a.quick else [16, 256, 1024, 4096, 16384]):
+            for K, N in shapes:
+                q = torch.randint(-128, 127, (M, K), dtype=torch.int8, device="cuda")
+                codes = torch.randint(-8, 7, (N, K), dtype=torch.int8, device="cuda")
+                w4 = ops.pack_w4(codes)
+                s_a = torch.rand(M, device="cuda") * 0.1
+                s_w = torch.rand(N, device="cuda") * 0.01
+                out = torch.empty(M, N, dtype=torch.float16, device="cuda")
+                sec, best = timeit(lambda: ops.w4a8_gemm(q, w4, s_a, s_w, N, out=out), flush=True)
+                rec("w4a8_gemm", f"M{M} K{K} N{N}", sec, best, bytes_=N * K // 2 + M * K + 2 * M * N + 4 * N,
+                    ops_=2 * M * N * K)
+                del q, codes, w4, out
+    if a.json:
+        json.dump(rows, open(a.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
