@@ -43,6 +43,26 @@ int num_sms();
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Division of a 31-bit index by a run-time constant with one multiply-high (Granlund-Montgomery;
+// the flattened (row, chunk) loops of the HBM-bound kernels would otherwise pay a 64-bit divide
+// per 16-byte chunk).
+struct FastDiv {
+  uint32_t mul, shr, d;
+  FastDiv() : mul(0), shr(0), d(1) {}
+  explicit FastDiv(uint32_t denom) : mul(0), shr(0), d(denom) {
+    if (denom > 1) {
+      uint32_t lg = 0;
+      while ((1u << lg) < denom) ++lg;
+      const uint32_t p = 31 + lg;
+      mul = (uint32_t)(((1ull << p) + denom - 1) / denom);
+      shr = p - 32;
+    }
+  }
+#ifdef __CUDACC__
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, mul) >> shr); }
+#endif
+};
+
 // ---- device helpers -------------------------------------------------------------------------
 #ifdef __CUDACC__
 
@@ -77,18 +97,21 @@ __device__ __forceinline__ void stg_stream8(void* p, const uint2& v) {
 #define MQ_RND_MAGIC 12582912.0f
 
 __device__ __forceinline__ float quant_code_exact(float x, float s, float lo, float hi) {
-  float q = rintf(__fdiv_rn(x, s));
+  // "+ zero_point" (an exact +0.0 for the symmetric types) turns a -0.0 quotient into +0.0
+  // (uniform.py:28); rintf keeps the sign of a tiny negative quotient (-0.0)
+  float q = rintf(__fadd_rn(__fdiv_rn(x, s), 0.f));
   return fminf(fmaxf(q, lo), hi);
 }
 
-// generic-width code as a float (fake-quant path, |hi| <= 2^19)
+// generic-width code as a float (fake-quant path, |hi| <= 2^19); the sign of a zero result
+// follows torch.round, see quant_code_exact
 __device__ __forceinline__ float quant_code(float x, float s, float inv, float lo, float hi) {
-  const float r = __fmul_rn(x, inv);
+  const float r = __fadd_rn(__fmul_rn(x, inv), 0.f);
   const float rc = fminf(fmaxf(r, lo), hi);
   const float rr = __fadd_rn(__fadd_rn(rc, MQ_RND_MAGIC), -MQ_RND_MAGIC);
   const float d = fabsf(fabsf(rc - rr) - 0.5f);
   if (d <= fmaxf(fabsf(rc), 1.f) * 1e-6f) return quant_code_exact(x, s, lo, hi);
-  return rr;
+  return copysignf(rr, rc);
 }
 
 // int8: returns the float whose low mantissa byte is the two's-complement code; `dist` is the

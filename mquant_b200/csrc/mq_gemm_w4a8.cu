@@ -23,6 +23,8 @@
 // 8192 MAC/clk/SM INT8 rate.  Bytes: N*K/2 (weights, L2 resident across m-tiles) + M*K + 2*M*N.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "mq_common.cuh"
 #include "mq_w4_layout.cuh"
 
@@ -140,6 +142,7 @@ struct Params {
   int64_t ldo;
   int M, N, K;
   int m_tiles, n_tiles, k_tiles;
+  unsigned dbg;  // MQ_GEMM_DEBUG bottleneck probes (results are garbage when non-zero)
 };
 
 __device__ __forceinline__ void unpack_store(uint32_t brow, int rsw, int j, const uint4& p) {
@@ -204,8 +207,12 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
         const int mb = t / p.n_tiles;
         for (int kb = 0; kb < p.k_tiles; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), A_STAGE);
-          tma_load_2d(sA + stage * A_STAGE, &tmap_a, kb * BK, mb * BM, full_bar(stage));
+          if (p.dbg & 2u) {
+            mbar_arrive(full_bar(stage));
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), A_STAGE);
+            tma_load_2d(sA + stage * A_STAGE, &tmap_a, kb * BK, mb * BM, full_bar(stage));
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -230,7 +237,8 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // +32 bytes along K inside the 128-byte swizzle atom = +2 in the 16-byte address field
-            umma_i8(tmem_d, adesc + 2u * k, bdesc + 2u * k, kInstrDesc, (uint32_t)((kb | k) != 0));
+            if (!(p.dbg & 8u))
+              umma_i8(tmem_d, adesc + 2u * k, bdesc + 2u * k, kInstrDesc, (uint32_t)((kb | k) != 0));
           }
           umma_commit(empty_bar(stage));
           if (kb == p.k_tiles - 1) umma_commit(tfull_bar(acc));
@@ -256,7 +264,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
     };
     uint4 bufA[4], bufB[4];
     auto load4 = [&](uint4 (&b)[4]) {
-      if (pf_valid()) {
+      if (pf_valid() && !(p.dbg & 1u)) {
         const uint8_t* src = pf_ptr();
 #pragma unroll
         for (int j = 0; j < 4; ++j) b[j] = ldg_stream(src + (size_t)j * kW4TileN * 16);
@@ -272,13 +280,18 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
       for (int kb = 0; kb < p.k_tiles; ++kb, ++it) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t brow = sB + stage * B_STAGE + brow_off;
+        const bool do_sts = !(p.dbg & (1u | 16u));
         if ((it & 1) == 0) {
+          if (do_sts) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) unpack_store(brow, rsw, j, bufA[j]);
+            for (int j = 0; j < 4; ++j) unpack_store(brow, rsw, j, bufA[j]);
+          }
           load4(bufA);
         } else {
+          if (do_sts) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) unpack_store(brow, rsw, j, bufB[j]);
+            for (int j = 0; j < 4; ++j) unpack_store(brow, rsw, j, bufB[j]);
+          }
           load4(bufB);
         }
         fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -335,7 +348,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
                 if (has_bias) val = __fadd_rn(val, ps[BN + col + e]);
                 y[e] = val;
               }
-              stg_stream(orow + col, pack8_f16(y));
+              if (!(p.dbg & 4u)) stg_stream(orow + col, pack8_f16(y));
             }
           }
         }
@@ -414,6 +427,8 @@ extern "C" int mq_w4a8_gemm(const int8_t* qa, int64_t lda, const uint8_t* w4, co
   p.m_tiles = (int)((M + BM - 1) / BM);
   p.n_tiles = (int)((N + BN - 1) / BN);
   p.k_tiles = (int)(K / BK);
+  const char* dbg_env = getenv("MQ_GEMM_DEBUG");
+  p.dbg = dbg_env ? (unsigned)atoi(dbg_env) : 0u;
   MQ_CUDA(cudaFuncSetAttribute(w4a8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());

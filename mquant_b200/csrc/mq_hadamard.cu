@@ -318,7 +318,7 @@ static int launch_warp(const HadArgs& a, cudaStream_t st) {
   constexpr int LANES = (N / 8) < 32 ? (N / 8) : 32;
   const int64_t warps = (a.M + (32 / LANES) - 1) / (32 / LANES);
   int64_t blocks = (warps + 3) / 4;
-  const int64_t cap = (int64_t)num_sms() * 8;
+  const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   fwht_warp_kernel<LOG_N><<<(int)blocks, 128, 0, st>>>(a);
   return MQ_OK;
@@ -330,7 +330,7 @@ static int launch_cta(const HadArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(N + N / 8) * sizeof(float);
   MQ_CUDA(cudaFuncSetAttribute(fwht_cta_kernel<LOG_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = a.M;
-  const int64_t cap = (int64_t)num_sms() * 4;
+  const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   fwht_cta_kernel<LOG_N><<<(int)blocks, 128, smem, st>>>(a);
   return MQ_OK;

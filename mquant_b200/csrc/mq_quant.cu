@@ -12,47 +12,65 @@
 
 namespace mq {
 
+// Work item = one 16-element chunk (two 128-bit loads, one 128-bit store).  Each thread takes
+// kUnroll chunks per trip and issues all of their loads before any arithmetic, so 4 x 16 B per
+// thread (~128 KB per SM at full occupancy) are in flight to cover HBM latency.
+constexpr int kQuantUnroll = 2;
+
 __global__ void __launch_bounds__(256)
 act_quant_i8_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* __restrict__ q,
                     float* __restrict__ srow_out, __half* __restrict__ x0_out,
                     const uint8_t* __restrict__ modality, const float* __restrict__ scales,
-                    int64_t M, int n_in, int n_out, unsigned flags) {
-  const int chunks_per_row = n_out >> 4;
-  const int64_t total = M * chunks_per_row;
+                    uint32_t total, FastDiv cpr, int n_in, int n_out, unsigned flags) {
   const float s_text = __ldg(scales), s_vis = __ldg(scales + 1);
   const float inv_text = __frcp_rn(s_text), inv_vis = __frcp_rn(s_vis);
-  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < total;
-       c += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = c / chunks_per_row;
-    const int col = (int)(c - m * chunks_per_row) << 4;
-    const bool vis = (modality != nullptr && modality[m] != 0);
-    const float s = vis ? s_vis : s_text;
-    const float inv = vis ? inv_vis : inv_text;
-    uint4 out = make_uint4(0u, 0u, 0u, 0u);
-    const __half* xr = x + m * ldx + col;
-    float f[8];
-    if (col + 8 <= n_in) {
-      uint4 v = ldg_stream(xr);
-      unpack8(v, f);
-      uint2 r = quant8(f, s, inv);
-      out.x = r.x;
-      out.y = r.y;
-      if (col == 0) {
-        if (flags & MQ_FLAG_SPLIT) {
-          x0_out[m] = reinterpret_cast<const __half*>(&v)[0];
-          out.x &= 0xffffff00u;
-        }
-        if (srow_out != nullptr) srow_out[m] = s;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += stride * kQuantUnroll) {
+    uint4 va[kQuantUnroll], vb[kQuantUnroll];
+    uint32_t row[kQuantUnroll];
+    int col[kQuantUnroll];
+    bool vis[kQuantUnroll];
+#pragma unroll
+    for (int u = 0; u < kQuantUnroll; ++u) {
+      const uint32_t c = c0 + u * stride;
+      va[u] = vb[u] = make_uint4(0u, 0u, 0u, 0u);
+      row[u] = 0;
+      col[u] = 0;
+      vis[u] = false;
+      if (c < total) {
+        row[u] = cpr.div(c);
+        col[u] = (int)(c - row[u] * cpr.d) << 4;
+        const __half* xr = x + (int64_t)row[u] * ldx + col[u];
+        if (col[u] + 8 <= n_in) va[u] = ldg_stream(xr);
+        if (col[u] + 16 <= n_in) vb[u] = ldg_stream(xr + 8);
+        vis[u] = (modality != nullptr) && (__ldg(modality + row[u]) != 0);
       }
     }
-    if (col + 16 <= n_in) {
-      uint4 v = ldg_stream(xr + 8);
-      unpack8(v, f);
-      uint2 r = quant8(f, s, inv);
+#pragma unroll
+    for (int u = 0; u < kQuantUnroll; ++u) {
+      const uint32_t c = c0 + u * stride;
+      if (c >= total) break;
+      const float s = vis[u] ? s_vis : s_text;
+      const float inv = vis[u] ? inv_vis : inv_text;
+      float f[8];
+      uint4 out;
+      unpack8(va[u], f);
+      uint2 r = quant8(f, s, inv);  // zero-padded columns quantise to code 0
+      out.x = r.x;
+      out.y = r.y;
+      unpack8(vb[u], f);
+      r = quant8(f, s, inv);
       out.z = r.x;
       out.w = r.y;
+      if (col[u] == 0) {
+        if (flags & MQ_FLAG_SPLIT) {
+          x0_out[row[u]] = reinterpret_cast<const __half*>(&va[u])[0];
+          out.x &= 0xffffff00u;
+        }
+        if (srow_out != nullptr) srow_out[row[u]] = s;
+      }
+      stg_stream(q + (int64_t)row[u] * n_out + col[u], out);
     }
-    stg_stream(q + m * (int64_t)n_out + col, out);
   }
 }
 
@@ -171,9 +189,11 @@ extern "C" int mq_act_quant_i8(const void* x, int64_t ldx, int8_t* q, float* sro
   MQ_REQUIRE(!(flags & MQ_FLAG_SPLIT) || x0_out, "mq_act_quant_i8: MQ_FLAG_SPLIT needs x0_out");
   if (M == 0) return MQ_OK;
   const int64_t chunks = M * (n_out / 16);
-  const int grid = mq::grid_for(chunks, 256, 8);
+  MQ_REQUIRE(chunks < (1ll << 31), "mq_act_quant_i8: M*n_out/16 = %lld exceeds 2^31 (split the batch)", (long long)chunks);
+  const int grid = mq::grid_for((chunks + mq::kQuantUnroll - 1) / mq::kQuantUnroll, 256, 8);
   mq::act_quant_i8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, ldx, q, srow_out, (__half*)x0_out, modality, scales, M, n_in, n_out, flags);
+      (const __half*)x, ldx, q, srow_out, (__half*)x0_out, modality, scales, (uint32_t)chunks,
+      mq::FastDiv((uint32_t)(n_out / 16)), n_in, n_out, flags);
   MQ_LAUNCH_CHECK("act_quant_i8_kernel");
   return MQ_OK;
 }

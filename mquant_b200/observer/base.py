@@ -19,7 +19,11 @@ class BaseObserver:
 
     # shared by minmax / percentile: reference minmax.py:30-52 == percentile.py:57-79
     def _params_from_minmax(self):
-        max_val, min_val = self.max_val, self.min_val
+        # Evaluated on the HOST with the reference's own torch expressions: CUDA torch divides by a
+        # scalar through a reciprocal multiply (1 ulp off in fp32), the CPU kernels divide.  The
+        # statistics are 2 (or 2*C) numbers and this runs once per calibration.
+        dev = self.max_val.device
+        max_val, min_val = self.max_val.cpu(), self.min_val.cpu()
         qmax, qmin = self.bit_type.upper_bound, self.bit_type.lower_bound
         if self.symmetric:
             # evaluated in the dtype of the statistics (fp16 for fp16 activations)
@@ -31,4 +35,4 @@ class BaseObserver:
             scale.clamp_(self.eps)
             zero_point = qmin - torch.round(min_val / scale)
             zero_point.clamp_(qmin, qmax)
-        return scale, zero_point
+        return scale.to(dev), zero_point.to(dev)

@@ -376,7 +376,7 @@ def matmul_hadU(X, transpose=False, dtype=np.float64):
     t = X.reshape(-1, K, n // K)
     t = fwht_last(t)
     if K > 1:
-        t = np.einsum("ij,bjk->bik", hadK.astype(dtype), t)
+        t = np.matmul(hadK.astype(dtype)[None], t)
     # ``torch.tensor(n).sqrt()`` is an fp32 value (hadamard_utils.py:100)
     return (t.reshape(X.shape) / dtype(np.sqrt(F32(n)))).astype(dtype)
 
@@ -402,7 +402,8 @@ def matmul_hadU_cuda(X, hadK=None, K=None, fp32_had=False):
         out = fht(work, scale)
     else:
         t = fht(work.reshape(-1, K, n // K), scale)
-        out = np.einsum("ij,bjk->bik", hadK.astype(F32), t.astype(F32)).astype(work.dtype)
+        # fp16 operands, fp32 accumulation (batched BLAS; same values as the einsum it replaces)
+        out = np.matmul(hadK.astype(F32)[None], t.astype(F32)).astype(work.dtype)
         out = out.reshape(X.shape)
     return out.astype(X.dtype)
 

@@ -51,6 +51,7 @@ CASES = [("plain", 256, 128, False, False), ("had256", 256, 64, True, False)]
 
 
 @pytest.mark.parametrize("tag,K_in,N_out,had,split", CASES)
+@torch.no_grad()
 def test_wrapper_fake_and_real_paths(qu, golden, tag, K_in, N_out, had, split):
     g = golden("wrapper")
     w = build_wrapper(qu, g, tag, K_in, N_out, had, split)
@@ -80,6 +81,7 @@ def test_wrapper_fake_and_real_paths(qu, golden, tag, K_in, N_out, had, split):
     assert np.array_equal(y_real.reshape(want.shape).view(np.uint16), want.view(np.uint16))
 
 
+@torch.no_grad()
 def test_qwenvl_mlp_down_proj_layer(qu):
     """Qwen-VL down_proj shape: K = 11008 = 172 x 64 online Hadamard, split off/on, MSQ."""
     from mquant_b200 import hadamard_utils as hu, msq, ops

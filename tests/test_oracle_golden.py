@@ -189,3 +189,22 @@ def test_dynamic_per_token(golden):
     codes = O.dynamic_quant_codes(x, s)
     y = (s[:, None] * codes).astype(np.float16).reshape(x.shape)
     assert np.array_equal(bits16(y), bits16(g["y"]))
+
+
+@pytest.mark.parametrize("tag", ["plain", "had256", "had344"])
+def test_torch_port_matches_reference(golden, tag):
+    """oracle/torch_port.py (what bench.py's CPU legs time) against the reference wrapper output."""
+    import torch
+
+    from oracle import torch_port as TP
+
+    g = golden("wrapper")
+    x = torch.from_numpy(g[f"{tag}_x"])
+    W = torch.from_numpy(g[f"{tag}_W"])
+    b = torch.from_numpy(g[f"{tag}_b"]) if f"{tag}_b" in g.files else None
+    hk, K = (None, None)
+    if tag != "plain":
+        hk, K = TP.hadK_tensor(x.shape[-1])
+    y = TP.qlinear_fake(x, W, b, torch.from_numpy(g[f"{tag}_act_scale"]), hk, K).numpy()
+    ref = g[f"{tag}_y"].astype(np.float32)
+    assert np.abs(y.astype(np.float32) - ref).max() <= 2.0 ** -9 * np.abs(ref).max() + 1e-3

@@ -1,0 +1,45 @@
+"""Run each hot kernel a few times at the headline shapes (ncu target).
+python tools/profile_target.py [gemm|quant|had|had172|minmax|all] [M]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mquant_b200 import hadamard_utils as hu, ops  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+M = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+scales = ops.make_scales(0.05, 0.11, "cuda")
+mod = (torch.rand(M, device="cuda") < 0.25).to(torch.uint8)
+reps = 3
+if which in ("gemm", "all"):
+    for K, N in ((4096, 11008), (11008, 4096), (4096, 4096)):
+        q = torch.randint(-128, 127, (M, K), dtype=torch.int8, device="cuda")
+        w4 = ops.pack_w4(torch.randint(-8, 7, (N, K), dtype=torch.int8, device="cuda"))
+        s_a = torch.rand(M, device="cuda") * 0.1
+        s_w = torch.rand(N, device="cuda") * 0.01
+        for _ in range(reps):
+            ops.w4a8_gemm(q, w4, s_a, s_w, N)
+        torch.cuda.synchronize()
+if which in ("quant", "all"):
+    x = (torch.randn(M, 4096, device="cuda") * 3).half()
+    for _ in range(reps):
+        ops.act_quant_i8(x, scales, mod)
+if which in ("minmax", "all"):
+    x = (torch.randn(M, 4096, device="cuda") * 3).half()
+    st = torch.zeros(2, device="cuda")
+    for _ in range(reps):
+        ops.observer_minmax(x, st)
+if which in ("had", "all"):
+    x = (torch.randn(M, 4096, device="cuda") * 3).half()
+    for _ in range(reps):
+        ops.hadamard(x, n=4096, scales=scales, modality=mod, want_codes=True, want_f16=False)
+if which in ("had172", "all"):
+    x = (torch.randn(M, 11008, device="cuda") * 3).half()
+    hk = hu.hadK_device(172, "cuda")
+    for _ in range(reps):
+        ops.hadamard(x, had_k=172, hadk=hk, n=11008, scales=scales, modality=mod, want_codes=True, want_f16=False)
+torch.cuda.synchronize()
+print("done", which, M)
