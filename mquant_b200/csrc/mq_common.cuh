@@ -114,18 +114,32 @@ __device__ __forceinline__ float quant_code(float x, float s, float inv, float l
   return copysignf(rr, rc);
 }
 
-// int8: returns the float whose low mantissa byte is the two's-complement code; `dist` is the
-// distance of the clamped quotient from the nearest half-integer
-__device__ __forceinline__ uint32_t q8_fast(float x, float inv, float& dist) {
-  const float r = __fmul_rn(x, inv);
-  const float rc = fminf(fmaxf(r, -128.f), 127.f);
-  const float t = __fadd_rn(rc, MQ_RND_MAGIC);
-  const float rr = __fadd_rn(t, -MQ_RND_MAGIC);
-  dist = fminf(dist, fabsf(fabsf(rc - rr) - 0.5f));
-  return __float_as_uint(t);
-}
 __device__ __forceinline__ uint32_t q8_exact(float x, float s) {
   return (uint32_t)__float2int_rn(quant_code_exact(x, s, -128.f, 127.f));
+}
+
+// ---- INT8 fast path ("bracketing") -----------------------------------------------------------
+// Per row-scale constants.  fl(x/s) lies strictly between x*inv_lo and x*inv_hi (inv_* = 1/s
+// moved 2^-22 apart; the error budget is 2^-24 each for 1/s, for the quotient rounding and for
+// forming inv_*).  Rounding to integer is monotone, so when both ends round to the same integer
+// -- one FFMA each against the 1.5*2^23 magic constant -- that integer IS rne(fl(x/s)).  The
+// (rare) chunks where some element disagrees are redone with the true division.  The clamp is
+// applied to x in the fp16 domain (two packed ops per pair): any fp16 value in
+// [126.6 s, 127.4 s] works as the upper limit because everything above it has code 127, and
+// fp16's 2^-11 spacing always leaves such a value (same for -128).
+struct QScale {
+  float s, inv_lo, inv_hi;
+  __half2 lim_lo, lim_hi;
+};
+__device__ __forceinline__ QScale make_qscale(float s) {
+  QScale q;
+  q.s = s;
+  const float inv = __frcp_rn(s);
+  q.inv_lo = __fmul_rn(inv, 1.0f - 2.384185791015625e-07f);
+  q.inv_hi = __fmul_rn(inv, 1.0f + 2.384185791015625e-07f);
+  q.lim_hi = __float2half2_rn(fminf(__fmul_rn(127.0f, s), 65504.f));
+  q.lim_lo = __float2half2_rn(fmaxf(__fmul_rn(-128.0f, s), -65504.f));
+  return q;
 }
 
 __device__ __forceinline__ uint32_t pack4_lowbytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -149,21 +163,38 @@ __device__ __forceinline__ uint4 pack8_f16(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
   return v;
 }
-// 8 floats -> 8 int8 codes (one uint2); bit-exact w.r.t. quant_code_exact
-__device__ __forceinline__ uint2 quant8(const float (&f)[8], float s, float inv) {
-  float dist = 1.f;
+// 8 halfs (one uint4) -> 8 int8 codes (one uint2); bit-exact w.r.t. quant_code_exact
+__device__ __forceinline__ uint2 quant8(const uint4& v, const QScale& q) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
   uint32_t t[8];
+  uint32_t diff = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) t[i] = q8_fast(f[i], inv, dist);
-  // 130 * 3 * 2^-24 = 2.3e-5 is the largest possible quotient error inside the clamp range
-  if (dist < 1e-4f) {
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(__hmin2(__hmax2(h[i], q.lim_lo), q.lim_hi));
+    const uint32_t a0 = __float_as_uint(__fmaf_rn(f.x, q.inv_lo, MQ_RND_MAGIC));
+    const uint32_t a1 = __float_as_uint(__fmaf_rn(f.x, q.inv_hi, MQ_RND_MAGIC));
+    const uint32_t b0 = __float_as_uint(__fmaf_rn(f.y, q.inv_lo, MQ_RND_MAGIC));
+    const uint32_t b1 = __float_as_uint(__fmaf_rn(f.y, q.inv_hi, MQ_RND_MAGIC));
+    diff |= (a0 ^ a1) | (b0 ^ b1);
+    t[2 * i] = a0;
+    t[2 * i + 1] = b0;
+  }
+  if (diff != 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = q8_exact(f[i], s);
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      t[2 * i] = q8_exact(f.x, q.s);
+      t[2 * i + 1] = q8_exact(f.y, q.s);
+    }
   }
   uint2 r;
   r.x = pack4_lowbytes(t[0], t[1], t[2], t[3]);
   r.y = pack4_lowbytes(t[4], t[5], t[6], t[7]);
   return r;
+}
+// same from 8 floats that already hold fp16 values (Hadamard epilogues)
+__device__ __forceinline__ uint2 quant8(const float (&f)[8], const QScale& q) {
+  return quant8(pack8_f16(f), q);
 }
 
 // fp16 round trip: the reference's rounding point after each Hadamard factor

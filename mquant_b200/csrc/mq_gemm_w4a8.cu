@@ -252,51 +252,41 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
     const int r = threadIdx.x - CONV_WARP0 * 32;  // row of the 256-row B tile
     const int rsw = r & 7;
     const uint32_t brow_off = (uint32_t)r * 128u;
-    // prefetch cursor (two k-blocks ahead of the conversion cursor)
+    // Packed weights come straight from L2 into registers, software-prefetched PF k-blocks ahead
+    // of the conversion cursor (PF == STAGES == 4: ~2000 cycles of cover for an L2 round trip,
+    // and the stage index of the unrolled slot is a compile-time constant).
+    constexpr int PF = STAGES;
     int pf_t = blockIdx.x, pf_kb = 0;
-    auto pf_valid = [&]() { return pf_t < total_tiles; };
-    auto pf_ptr = [&]() {
-      const int nb = pf_t % p.n_tiles;
-      return p.w4 + w4_blob_offset(nb, pf_kb, p.k_tiles) + (size_t)r * 16;
-    };
-    auto pf_advance = [&]() {
-      if (++pf_kb == p.k_tiles) { pf_kb = 0; pf_t += gridDim.x; }
-    };
-    uint4 bufA[4], bufB[4];
+    uint4 buf[PF][4];
     auto load4 = [&](uint4 (&b)[4]) {
-      if (pf_valid() && !(p.dbg & 1u)) {
-        const uint8_t* src = pf_ptr();
+      if (pf_t < total_tiles && !(p.dbg & 1u)) {
+        const int nb = pf_t % p.n_tiles;
+        const uint8_t* src = p.w4 + w4_blob_offset(nb, pf_kb, p.k_tiles) + (size_t)r * 16;
 #pragma unroll
         for (int j = 0; j < 4; ++j) b[j] = ldg_stream(src + (size_t)j * kW4TileN * 16);
       }
-      pf_advance();
+      if (++pf_kb == p.k_tiles) { pf_kb = 0; pf_t += gridDim.x; }
     };
-    load4(bufA);
-    load4(bufB);
-    int stage = 0;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) load4(buf[u]);
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_it = my_tiles * p.k_tiles;
+    const bool do_sts = !(p.dbg & (1u | 16u));
     uint32_t phase = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      for (int kb = 0; kb < p.k_tiles; ++kb, ++it) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t brow = sB + stage * B_STAGE + brow_off;
-        const bool do_sts = !(p.dbg & (1u | 16u));
-        if ((it & 1) == 0) {
+    for (int it0 = 0; it0 < total_it; it0 += PF, phase ^= 1u) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        if (it0 + u < total_it) {
+          mbar_wait(empty_bar(u), phase ^ 1u);
+          const uint32_t brow = sB + u * B_STAGE + brow_off;
           if (do_sts) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) unpack_store(brow, rsw, j, bufA[j]);
+            for (int j = 0; j < 4; ++j) unpack_store(brow, rsw, j, buf[u][j]);
           }
-          load4(bufA);
-        } else {
-          if (do_sts) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) unpack_store(brow, rsw, j, bufB[j]);
-          }
-          load4(bufB);
+          load4(buf[u]);
+          fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+          mbar_arrive(full_bar(u));
         }
-        fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(full_bar(stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= EPI_WARP0) {

@@ -108,7 +108,7 @@ __device__ __forceinline__ void emit8(const HadArgs& a, int64_t m, int col, floa
   }
   if (a.y != nullptr) stg_stream(a.y + m * (int64_t)a.n + col, pack8_f16(f));
   if (a.q != nullptr) {
-    uint2 r = quant8(f, s_act, __frcp_rn(s_act));
+    uint2 r = quant8(f, make_qscale(s_act));
     if (col == 0 && (a.flags & MQ_FLAG_SPLIT)) {
       a.x0_out[m] = __float2half_rn(f[0]);
       r.x &= 0xffffff00u;

@@ -30,21 +30,34 @@ minmax_tensor_kernel(const __half* __restrict__ x, int64_t ldx, int64_t M, int C
   const int64_t total = M * chunks_per_row;
   __half2 mx = __float2half2_rn(0.f), mn = __float2half2_rn(0.f);
   const bool contiguous = (ldx == C);
-  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < total;
-       c += (int64_t)gridDim.x * blockDim.x) {
-    const __half* p;
-    if (contiguous) {
-      p = x + c * 8;
-    } else {
-      const int64_t m = c / chunks_per_row;
-      p = x + m * ldx + ((c - m * chunks_per_row) << 3);
-    }
-    const uint4 v = ldg_stream(p);
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // 4 independent 128-bit loads in flight per thread (pure streaming reduction: latency bound
+  // otherwise)
+  for (int64_t c0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c0 < total; c0 += 4 * stride) {
+    uint4 v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      mx = __hmax2(mx, h[i]);
-      mn = __hmin2(mn, h[i]);
+    for (int u = 0; u < 4; ++u) {
+      const int64_t c = c0 + u * stride;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (c < total) {
+        const __half* p;
+        if (contiguous) {
+          p = x + c * 8;
+        } else {
+          const int64_t m = c / chunks_per_row;
+          p = x + m * ldx + ((c - m * chunks_per_row) << 3);
+        }
+        v[u] = ldg_stream(p);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        mx = __hmax2(mx, h[i]);
+        mn = __hmin2(mn, h[i]);
+      }
     }
   }
   float fmx = fmaxf(__low2float(mx), __high2float(mx));

@@ -22,8 +22,7 @@ act_quant_i8_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* __restric
                     float* __restrict__ srow_out, __half* __restrict__ x0_out,
                     const uint8_t* __restrict__ modality, const float* __restrict__ scales,
                     uint32_t total, FastDiv cpr, int n_in, int n_out, unsigned flags) {
-  const float s_text = __ldg(scales), s_vis = __ldg(scales + 1);
-  const float inv_text = __frcp_rn(s_text), inv_vis = __frcp_rn(s_vis);
+  const QScale q_text = make_qscale(__ldg(scales)), q_vis = make_qscale(__ldg(scales + 1));
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += stride * kQuantUnroll) {
     uint4 va[kQuantUnroll], vb[kQuantUnroll];
@@ -50,16 +49,12 @@ act_quant_i8_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* __restric
     for (int u = 0; u < kQuantUnroll; ++u) {
       const uint32_t c = c0 + u * stride;
       if (c >= total) break;
-      const float s = vis[u] ? s_vis : s_text;
-      const float inv = vis[u] ? inv_vis : inv_text;
-      float f[8];
+      const QScale& qs = vis[u] ? q_vis : q_text;
       uint4 out;
-      unpack8(va[u], f);
-      uint2 r = quant8(f, s, inv);  // zero-padded columns quantise to code 0
+      uint2 r = quant8(va[u], qs);  // zero-padded columns quantise to code 0
       out.x = r.x;
       out.y = r.y;
-      unpack8(vb[u], f);
-      r = quant8(f, s, inv);
+      r = quant8(vb[u], qs);
       out.z = r.x;
       out.w = r.y;
       if (col[u] == 0) {
@@ -67,7 +62,7 @@ act_quant_i8_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* __restric
           x0_out[row[u]] = reinterpret_cast<const __half*>(&va[u])[0];
           out.x &= 0xffffff00u;
         }
-        if (srow_out != nullptr) srow_out[row[u]] = s;
+        if (srow_out != nullptr) srow_out[row[u]] = qs.s;
       }
       stg_stream(q + (int64_t)row[u] * n_out + col[u], out);
     }
@@ -143,21 +138,16 @@ act_quant_i8_dynamic_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* _
     const float xmax = fmaxf(fabsf(xmin), xmax0);
     const float s = (xmax == 0.f) ? 1.f : __fdiv_rn(xmax, 127.f);
     if (lane == 0) srow_out[m] = s;
-    const float inv = __frcp_rn(s);
+    const QScale qs = make_qscale(s);
     for (int col = lane << 4; col < n_out; col += 512) {
       uint4 out = make_uint4(0u, 0u, 0u, 0u);
-      float f[8];
       if (col + 8 <= n_in) {
-        uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + col));
-        unpack8(v, f);
-        uint2 r = quant8(f, s, inv);
+        uint2 r = quant8(__ldg(reinterpret_cast<const uint4*>(xr + col)), qs);
         out.x = r.x;
         out.y = r.y;
       }
       if (col + 16 <= n_in) {
-        uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + col + 8));
-        unpack8(v, f);
-        uint2 r = quant8(f, s, inv);
+        uint2 r = quant8(__ldg(reinterpret_cast<const uint4*>(xr + col + 8)), qs);
         out.z = r.x;
         out.w = r.y;
       }
