@@ -1,5 +1,6 @@
 // Library-wide plumbing: version, thread-local error string, device info.
 #include "mq_common.cuh"
+#include "mq_tc.cuh"
 
 #include <cstring>
 
@@ -32,6 +33,20 @@ int num_sms() {
   }
   return cached;
 }
+
+namespace tc {
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+}  // namespace tc
 
 }  // namespace mq
 

@@ -13,11 +13,16 @@
 //   warp 1      MMA issuer: 4 x tcgen05.mma (M128 N256 K32) per k-block, commits free the stage
 //   warp 2      TMEM allocator (512 columns = 2 accumulator buffers of 256)
 //   warps 4-7   epilogue: tcgen05.ld 32x32b.x32, scale/bias, 64-byte row segments to HBM
-//   warps 8-15  weight converters: packed INT4 (mq_w4_layout.cuh) global -> registers (software
-//               prefetched two k-blocks ahead) -> two logic ops per 8 weights -> INT8 (x16) in the
-//               K-major SWIZZLE_128B layout -> fence.proxy.async -> mbarrier arrive
-// Pipelines: smem ring of 4 stages (full: TMA tx + 256 converter arrivals; empty: tcgen05.commit),
-// TMEM double buffer (tmem_full: commit after the last k-block; tmem_empty: 128 epilogue arrivals).
+//   warp 3      packed-weight producer: one 16 KB cp.async.bulk per k-block into a staging ring
+//               (mq_w4_layout.cuh makes each (n-block, k-block) blob contiguous)
+//   warps 8-15  weight converters: staging -> registers -> two logic ops per 8 weights -> INT8
+//               (x16) in the K-major SWIZZLE_128B layout -> fence.proxy.async -> mbarrier arrive.
+//               (A first version prefetched the packed weights with LDG into registers; the proxy
+//               fence is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in SASS and stalled on the outstanding
+//               LDGs every k-block: 1.35 -> see profiles/ for the staged version.)
+// Pipelines: A/B ring of 3 stages (full: TMA tx + 256 converter arrivals; empty: tcgen05.commit),
+// packed-weight ring of 4 (wfull: bulk-copy tx; wempty: 256 converter arrivals), TMEM double
+// buffer (tmem_full: commit after the last k-block; tmem_empty: 128 epilogue arrivals).
 //
 // Roofline: tensor pipe.  ops = 2*M*N*K; one k-block (128x256x128 MACs) is 512 cycles at the
 // 8192 MAC/clk/SM INT8 rate.  Bytes: N*K/2 (weights, L2 resident across m-tiles) + M*K + 2*M*N.
@@ -26,18 +31,22 @@
 #include <cstdlib>
 
 #include "mq_common.cuh"
+#include "mq_tc.cuh"
 #include "mq_w4_layout.cuh"
 
 namespace mq {
 namespace gemm {
+using namespace mq::tc;
 
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 128;  // bytes == int8 elements
 constexpr int UMMA_K = 32;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;   // A (TMA) + B (converted INT8) ring
+constexpr int WSTAGES = 4;  // packed-INT4 staging ring (bulk async copies)
 constexpr int A_STAGE = BM * BK;  // 16 KB
 constexpr int B_STAGE = BN * BK;  // 32 KB
+constexpr int W_STAGE = kW4BlobBytes;  // 16 KB
 constexpr int NUM_THREADS = 512;
 constexpr int EPI_WARP0 = 4;
 constexpr int CONV_WARP0 = 8;
@@ -47,70 +56,12 @@ constexpr int TMEM_COLS = 512;
 // dynamic shared memory carve-up (base aligned to 1024 for SWIZZLE_128B)
 constexpr int SM_A = 0;
 constexpr int SM_B = SM_A + STAGES * A_STAGE;
-constexpr int SM_PARAM = SM_B + STAGES * B_STAGE;       // 2 x {s_w16[256], bias[256], w0[256]} fp32
-constexpr int SM_BAR = SM_PARAM + 2 * 3 * BN * 4;       // full[4] empty[4] tfull[2] tempty[2]
-constexpr int SM_TMEMPTR = SM_BAR + (2 * STAGES + 4) * 8;
+constexpr int SM_W = SM_B + STAGES * B_STAGE;
+constexpr int SM_PARAM = SM_W + WSTAGES * W_STAGE;      // 2 x {s_w16[256], bias[256], w0[256]} fp32
+constexpr int SM_BAR = SM_PARAM + 2 * 3 * BN * 4;       // full[S] empty[S] wfull[W] wempty[W] tfull[2] tempty[2]
+constexpr int SM_TMEMPTR = SM_BAR + (2 * STAGES + 2 * WSTAGES + 4) * 8;
 constexpr int SM_TOTAL = SM_TMEMPTR + 16;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;  // slack for manual 1024-byte alignment
-
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
-      "%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row x 128-byte atoms, SBO = 1024 B
 // between atoms along M/N, one atom along K (LBO unused).  cute::UMMA::SmemDescriptor bit layout.
@@ -167,8 +118,11 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
   const uint32_t bar0 = base + SM_BAR;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  auto wfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto wempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + WSTAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 * WSTAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 * WSTAGES + 2 + a); };
+  const uint32_t sW = base + SM_W;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEMPTR);
 
   const int warp = threadIdx.x >> 5;
@@ -180,6 +134,10 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1 + NUM_CONV);
       mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < WSTAGES; ++s) {
+      mbar_init(wfull_bar(s), 1);
+      mbar_init(wempty_bar(s), NUM_CONV);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -214,6 +172,22 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
             tma_load_2d(sA + stage * A_STAGE, &tmap_a, kb * BK, mb * BM, full_bar(stage));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== packed-weight producer =====================
+    // one 16 KB bulk async copy per k-block: the tile-major layout makes every blob contiguous
+    if (lane == 0 && !(p.dbg & 1u)) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nb = t % p.n_tiles;
+        for (int kb = 0; kb < p.k_tiles; ++kb) {
+          mbar_wait(wempty_bar(ws), wphase ^ 1u);
+          mbar_arrive_expect_tx(wfull_bar(ws), W_STAGE);
+          bulk_load(sW + ws * W_STAGE, p.w4 + w4_blob_offset(nb, kb, p.k_tiles), W_STAGE, wfull_bar(ws));
+          if (++ws == WSTAGES) { ws = 0; wphase ^= 1u; }
         }
       }
     }
@@ -252,42 +226,38 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
     const int r = threadIdx.x - CONV_WARP0 * 32;  // row of the 256-row B tile
     const int rsw = r & 7;
     const uint32_t brow_off = (uint32_t)r * 128u;
-    // Packed weights come straight from L2 into registers, software-prefetched PF k-blocks ahead
-    // of the conversion cursor (PF == STAGES == 4: ~2000 cycles of cover for an L2 round trip,
-    // and the stage index of the unrolled slot is a compile-time constant).
-    constexpr int PF = STAGES;
-    int pf_t = blockIdx.x, pf_kb = 0;
-    uint4 buf[PF][4];
-    auto load4 = [&](uint4 (&b)[4]) {
-      if (pf_t < total_tiles && !(p.dbg & 1u)) {
-        const int nb = pf_t % p.n_tiles;
-        const uint8_t* src = p.w4 + w4_blob_offset(nb, pf_kb, p.k_tiles) + (size_t)r * 16;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = ldg_stream(src + (size_t)j * kW4TileN * 16);
-      }
-      if (++pf_kb == p.k_tiles) { pf_kb = 0; pf_t += gridDim.x; }
-    };
-#pragma unroll
-    for (int u = 0; u < PF; ++u) load4(buf[u]);
+    // staging (packed INT4, landed by the bulk copy) -> registers -> INT8 x16 -> B stage.
+    // Nothing but shared-memory traffic is outstanding when the proxy fence (MEMBAR.ALL.CTA +
+    // FENCE.VIEW.ASYNC) executes, so it costs tens of cycles, not an L2 round trip.
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_it = my_tiles * p.k_tiles;
+    const bool do_w = !(p.dbg & 1u);
     const bool do_sts = !(p.dbg & (1u | 16u));
-    uint32_t phase = 0;
-    for (int it0 = 0; it0 < total_it; it0 += PF, phase ^= 1u) {
+    int stage = 0, ws = 0;
+    uint32_t phase = 0, wphase = 0;
+    for (int it = 0; it < total_it; ++it) {
+      uint4 pk[4];
+      if (do_w) {
+        mbar_wait(wfull_bar(ws), wphase);
+        const uint32_t src = sW + ws * W_STAGE + (uint32_t)r * 16u;
 #pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        if (it0 + u < total_it) {
-          mbar_wait(empty_bar(u), phase ^ 1u);
-          const uint32_t brow = sB + u * B_STAGE + brow_off;
-          if (do_sts) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) unpack_store(brow, rsw, j, buf[u][j]);
-          }
-          load4(buf[u]);
-          fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-          mbar_arrive(full_bar(u));
+        for (int j = 0; j < 4; ++j) {
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(pk[j].x), "=r"(pk[j].y), "=r"(pk[j].z), "=r"(pk[j].w)
+                       : "r"(src + (uint32_t)j * kW4TileN * 16u));
         }
       }
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t brow = sB + stage * B_STAGE + brow_off;
+      if (do_sts) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) unpack_store(brow, rsw, j, pk[j]);
+      }
+      fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(full_bar(stage));
+      if (do_w) mbar_arrive(wempty_bar(ws));  // the loads above have been consumed by the stores
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      if (++ws == WSTAGES) { ws = 0; wphase ^= 1u; }
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue =====================
@@ -355,23 +325,6 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
   }
 }
 
-// ---- host side ------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
-
 }  // namespace gemm
 }  // namespace mq
 
@@ -392,7 +345,7 @@ extern "C" int mq_w4a8_gemm(const int8_t* qa, int64_t lda, const uint8_t* w4, co
   MQ_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "mq_w4a8_gemm: dimension exceeds 2^31");
   if (M == 0) return MQ_OK;
 
-  EncodeTiledFn encode = get_encode_fn();
+  tc::EncodeTiledFn encode = tc::get_encode_fn();
   if (encode == nullptr) {
     set_error("mq_w4a8_gemm: cuTensorMapEncodeTiled is not available from the driver");
     return MQ_ERR_CUDA;

@@ -12,30 +12,15 @@
 //   fwht_warp_kernel   n = 64..2048 (had_k = 1): one (sub-)warp per row, registers + shuffles
 //   fwht_cta_kernel    n = 4096 / 8192 (had_k = 1): 4 warps per row, one shared-memory exchange
 //   hadk_simt_kernel   had_k > 1: FHT_P per segment in registers, hadK factor on CUDA cores from
-//                      shared memory (correctness baseline; the tcgen05 version supersedes it)
+//                      shared memory.  Correctness baseline and fallback (fp16 output for
+//                      calibration, --fp32_had, n/had_k = 256/512); the hot path (codes only,
+//                      n/had_k = 64 or 128) runs mq_hadamard_tc.cu on tcgen05.
 //
 // HBM traffic per token: 2*n_in read + n written (codes) [+ 2*n if y_f16 is requested].
 #include "mq_common.cuh"
+#include "mq_hadamard_args.cuh"
 
 namespace mq {
-
-struct HadArgs {
-  const __half* x;
-  int64_t ldx;
-  int8_t* q;        // nullable
-  __half* y;        // nullable
-  float* srow_out;  // nullable
-  __half* x0_out;   // nullable (split)
-  const uint8_t* modality;
-  const float* scales;  // nullable when q == nullptr
-  const __half* hadk;   // [had_k, had_k] +-1
-  int had_k;
-  int64_t M;
-  int n_in;
-  int n;
-  unsigned flags;
-  float norm;  // float32(1/sqrt(n))
-};
 
 // in-register butterflies over the 8 elements of each chunk (index bits 0..2) and across the
 // R chunks a thread owns (the top log2(R) index bits)
@@ -390,6 +375,8 @@ extern "C" int mq_hadamard_quant_i8(const void* x, int64_t ldx, int8_t* q, void*
         set_error("mq_hadamard_quant_i8: power-of-two n=%d outside [64, 8192]", n);
         return MQ_ERR_UNSUPPORTED;
     }
+  } else if (hadk_tc_supported(a)) {
+    rc = launch_hadk_tc(a, st);  // both Kronecker factors on tcgen05
   } else {
     switch (logp) {
       case 3: case 4: case 5:

@@ -1,0 +1,30 @@
+// Argument block shared by the Hadamard kernels.
+#pragma once
+#include "mq_common.cuh"
+
+namespace mq {
+
+struct HadArgs {
+  const __half* x;
+  int64_t ldx;
+  int8_t* q;        // nullable
+  __half* y;        // nullable
+  float* srow_out;  // nullable
+  __half* x0_out;   // nullable (split)
+  const uint8_t* modality;
+  const float* scales;  // nullable when q == nullptr
+  const __half* hadk;   // [had_k, had_k] +-1
+  int had_k;
+  int64_t M;
+  int n_in;
+  int n;
+  unsigned flags;
+  float norm;  // float32(1/sqrt(n))
+};
+
+
+// mq_hadamard_tc.cu
+bool hadk_tc_supported(const HadArgs& a);
+int launch_hadk_tc(const HadArgs& a, cudaStream_t st);
+
+}  // namespace mq

@@ -269,6 +269,44 @@ def test_hadamard_nonpow2(ops, n, n_in):
         had_check(ops, x, n, k, s, modality=mod, s_vis=np.float32(np.float16(s * 2.5)))
 
 
+@pytest.mark.parametrize("n,n_in,M", [(11008, 11008, 9), (11008, 11008, 300), (13824, 13696, 5),
+                                      (19968, 18944, 7), (5120, 5120, 33), (3584, 3584, 130)])
+def test_hadamard_nonpow2_tensor_core_path(ops, n, n_in, M):
+    """codes-only requests with n/had_k in {64,128} run both Kronecker factors on tcgen05
+    (mq_hadamard_tc.cu); compare with the CUDA-core kernel and with the oracle."""
+    from mquant_b200 import hadamard_utils as hu
+
+    k = O.get_hadK(n)[1]
+    rng = np.random.default_rng(n + M)
+    x = rnd_act(rng, M, n_in)
+    s = np.float32(np.float16(np.abs(x.astype(np.float32)).max() / 127 / 4))
+    s_vis = np.float32(np.float16(s * 2.5))
+    mod = (rng.random(M) < 0.5).astype(np.uint8)
+    hk = hu.hadK_device(k, "cuda")
+    scales = ops.make_scales(float(s), float(s_vis), "cuda")
+    xd, md = dev(x), dev(mod)
+    for split in (False, True):
+        tc = ops.hadamard(xd, had_k=k, hadk=hk, n=n, scales=scales, modality=md, want_codes=True,
+                          want_f16=False, split=split)
+        ref = ops.hadamard(xd, had_k=k, hadk=hk, n=n, scales=scales, modality=md, want_codes=True,
+                           want_f16=True, split=split)  # fp16 output requested -> CUDA-core kernel
+        q_tc, q_ref = host(tc["q"]).astype(np.int32), host(ref["q"]).astype(np.int32)
+        d = np.abs(q_tc - q_ref)
+        assert d.max() <= 1, d.max()
+        assert (d > 0).mean() < 2e-3, (d > 0).mean()
+        assert np.array_equal(host(tc["s_row"]), O.msq_token_scales(mod, s, s_vis))
+        if split:
+            assert not q_tc[:, 0].any()
+            x0_tc, x0_ref = host(tc["x0"]).astype(np.float32), host(ref["x0"]).astype(np.float32)
+            assert np.abs(x0_tc - x0_ref).max() <= 2.0 ** -9 * max(1.0, np.abs(x0_ref).max())
+        else:
+            yo = O.matmul_hadU_cuda(O.pad_last(x, n))
+            oc = O.msq_quant_codes(yo, mod, s, s_vis).astype(np.int32)
+            d = np.abs(q_tc - oc)
+            assert d.max() <= 1
+            assert (d > 0).mean() < 2e-3, (d > 0).mean()
+
+
 def test_matmul_hadU_cuda_api(ops, golden):
     from mquant_b200 import hadamard_utils as hu
 
