@@ -166,25 +166,27 @@ __device__ __forceinline__ uint4 pack8_f16(const float (&f)[8]) {
 // 8 halfs (one uint4) -> 8 int8 codes (one uint2); bit-exact w.r.t. quant_code_exact
 __device__ __forceinline__ uint2 quant8(const uint4& v, const QScale& q) {
   const __half2* h = reinterpret_cast<const __half2*>(&v);
-  uint32_t t[8];
+  uint32_t t[8], d[8];
   uint32_t diff = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float2 f = __half22float2(__hmin2(__hmax2(h[i], q.lim_lo), q.lim_hi));
-    const uint32_t a0 = __float_as_uint(__fmaf_rn(f.x, q.inv_lo, MQ_RND_MAGIC));
-    const uint32_t a1 = __float_as_uint(__fmaf_rn(f.x, q.inv_hi, MQ_RND_MAGIC));
-    const uint32_t b0 = __float_as_uint(__fmaf_rn(f.y, q.inv_lo, MQ_RND_MAGIC));
-    const uint32_t b1 = __float_as_uint(__fmaf_rn(f.y, q.inv_hi, MQ_RND_MAGIC));
-    diff |= (a0 ^ a1) | (b0 ^ b1);
-    t[2 * i] = a0;
-    t[2 * i + 1] = b0;
+    t[2 * i] = __float_as_uint(__fmaf_rn(f.x, q.inv_lo, MQ_RND_MAGIC));
+    t[2 * i + 1] = __float_as_uint(__fmaf_rn(f.y, q.inv_lo, MQ_RND_MAGIC));
+    d[2 * i] = t[2 * i] ^ __float_as_uint(__fmaf_rn(f.x, q.inv_hi, MQ_RND_MAGIC));
+    d[2 * i + 1] = t[2 * i + 1] ^ __float_as_uint(__fmaf_rn(f.y, q.inv_hi, MQ_RND_MAGIC));
+    diff |= d[2 * i] | d[2 * i + 1];
   }
+  // Undecided elements (the bracket straddles a half-integer: mostly quotients that round to an
+  // exact tie, ~1e-4 .. 1e-2 of elements depending on how "round" the scale is) take the true
+  // division, element by element so that a warp pays only for the lanes that need it.
   if (diff != 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __half22float2(h[i]);
-      t[2 * i] = q8_exact(f.x, q.s);
-      t[2 * i + 1] = q8_exact(f.y, q.s);
+    for (int i = 0; i < 8; ++i) {
+      if (d[i] != 0) {
+        const float x = __half2float(reinterpret_cast<const __half*>(&v)[i]);
+        t[i] = q8_exact(x, q.s);
+      }
     }
   }
   uint2 r;

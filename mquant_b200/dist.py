@@ -97,4 +97,10 @@ def merge_calibration(model, group=None, channels_hint=None):
     merge_observer_states([o.state for o in live], group)
     for o in live:
         o._refresh()
+    # the scales were last derived from rank-local statistics: recompute them from the merged ones
+    for _, layer in find_qlayers(model, layers=[ActQuantWrapper]).items():
+        q = layer.quantizer
+        if getattr(q, "static", False) and (q.observer.max_val is not None or
+                                            (q.msq and q.observer_visual.max_val is not None)):
+            q.update_quantization_params()
     return len(live)

@@ -11,7 +11,7 @@ from mquant_b200 import hadamard_utils as hu, ops  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
-scales = ops.make_scales(0.05, 0.11, "cuda")
+scales = ops.make_scales(float(torch.tensor(0.1134, dtype=torch.float16)), float(torch.tensor(0.2871, dtype=torch.float16)), "cuda")
 mod = (torch.rand(M, device="cuda") < 0.25).to(torch.uint8)
 reps = 3
 if which in ("gemm", "all"):
