@@ -1,0 +1,57 @@
+// Pieces shared by the 1-CTA and 2-CTA W4A8 GEMM kernels.
+#pragma once
+#include <cuda.h>
+
+#include "mq_common.cuh"
+#include "mq_tc.cuh"
+#include "mq_w4_layout.cuh"
+
+namespace mq {
+namespace gemm {
+using namespace mq::tc;
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row x 128-byte atoms, SBO = 1024 B
+// between atoms along M/N, one atom along K (LBO unused).  cute::UMMA::SmemDescriptor bit layout.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)0 << 16;                      // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+
+struct Params {
+  const uint8_t* w4;
+  const float* s_a;
+  int s_a_per_row;
+  const float* s_w;
+  const __half* bias;
+  const __half* x0;
+  const __half* w0;
+  __half* out;
+  int64_t ldo;
+  int M, N, K;
+  int m_tiles, n_tiles, k_tiles;
+  unsigned dbg;  // MQ_GEMM_DEBUG bottleneck probes (results are garbage when non-zero)
+};
+
+__device__ __forceinline__ void unpack_store(uint32_t brow, int rsw, int j, const uint4& p) {
+  // low nibbles -> k = 32j .. 32j+15 (16-byte chunk 2j), high nibbles -> chunk 2j+1; values x16
+  const uint32_t lo0 = (p.x << 4) & 0xF0F0F0F0u, lo1 = (p.y << 4) & 0xF0F0F0F0u;
+  const uint32_t lo2 = (p.z << 4) & 0xF0F0F0F0u, lo3 = (p.w << 4) & 0xF0F0F0F0u;
+  const uint32_t hi0 = p.x & 0xF0F0F0F0u, hi1 = p.y & 0xF0F0F0F0u;
+  const uint32_t hi2 = p.z & 0xF0F0F0F0u, hi3 = p.w & 0xF0F0F0F0u;
+  const uint32_t a0 = brow + ((uint32_t)((2 * j) ^ rsw) << 4);
+  const uint32_t a1 = brow + ((uint32_t)((2 * j + 1) ^ rsw) << 4);
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(lo0), "r"(lo1), "r"(lo2), "r"(lo3) : "memory");
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(hi0), "r"(hi1), "r"(hi2), "r"(hi3) : "memory");
+}
+
+
+// mq_gemm_w4a8_2cta.cu: cta_group::2 kernel (256 x 256 tile per CTA pair)
+int launch_w4a8_gemm_2cta(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st);
+
+}  // namespace gemm
+}  // namespace mq

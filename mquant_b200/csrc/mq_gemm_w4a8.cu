@@ -30,9 +30,7 @@
 
 #include <cstdlib>
 
-#include "mq_common.cuh"
-#include "mq_tc.cuh"
-#include "mq_w4_layout.cuh"
+#include "mq_gemm_common.cuh"
 
 namespace mq {
 namespace gemm {
@@ -63,50 +61,11 @@ constexpr int SM_TMEMPTR = SM_BAR + (2 * STAGES + 2 * WSTAGES + 4) * 8;
 constexpr int SM_TOTAL = SM_TMEMPTR + 16;
 constexpr int SM_ALLOC = SM_TOTAL + 1024;  // slack for manual 1024-byte alignment
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row x 128-byte atoms, SBO = 1024 B
-// between atoms along M/N, one atom along K (LBO unused).  cute::UMMA::SmemDescriptor bit layout.
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address
-  d |= (uint64_t)0 << 16;                      // leading byte offset (ignored for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset
-  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
-  return d;
-}
-
 // cute::UMMA::InstrDescriptor for kind::i8, S32 accumulate, both operands K-major
 constexpr uint32_t kInstrDesc = (2u << 4)      // c_format = S32
                                 | (1u << 7)    // a_format = INT8
                                 | (1u << 10)   // b_format = INT8
                                 | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-struct Params {
-  const uint8_t* w4;
-  const float* s_a;
-  int s_a_per_row;
-  const float* s_w;
-  const __half* bias;
-  const __half* x0;
-  const __half* w0;
-  __half* out;
-  int64_t ldo;
-  int M, N, K;
-  int m_tiles, n_tiles, k_tiles;
-  unsigned dbg;  // MQ_GEMM_DEBUG bottleneck probes (results are garbage when non-zero)
-};
-
-__device__ __forceinline__ void unpack_store(uint32_t brow, int rsw, int j, const uint4& p) {
-  // low nibbles -> k = 32j .. 32j+15 (16-byte chunk 2j), high nibbles -> chunk 2j+1; values x16
-  const uint32_t lo0 = (p.x << 4) & 0xF0F0F0F0u, lo1 = (p.y << 4) & 0xF0F0F0F0u;
-  const uint32_t lo2 = (p.z << 4) & 0xF0F0F0F0u, lo3 = (p.w << 4) & 0xF0F0F0F0u;
-  const uint32_t hi0 = p.x & 0xF0F0F0F0u, hi1 = p.y & 0xF0F0F0F0u;
-  const uint32_t hi2 = p.z & 0xF0F0F0F0u, hi3 = p.w & 0xF0F0F0F0u;
-  const uint32_t a0 = brow + ((uint32_t)((2 * j) ^ rsw) << 4);
-  const uint32_t a1 = brow + ((uint32_t)((2 * j + 1) ^ rsw) << 4);
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(lo0), "r"(lo1), "r"(lo2), "r"(lo3) : "memory");
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(hi0), "r"(hi1), "r"(hi2), "r"(hi3) : "memory");
-}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
@@ -372,6 +331,14 @@ extern "C" int mq_w4a8_gemm(const int8_t* qa, int64_t lda, const uint8_t* w4, co
   p.k_tiles = (int)(K / BK);
   const char* dbg_env = getenv("MQ_GEMM_DEBUG");
   p.dbg = dbg_env ? (unsigned)atoi(dbg_env) : 0u;
+  // M > 128: CTA pairs (cta_group::2, 256 x 256 tiles); small M keeps the 1-CTA kernel
+  const char* one_env = getenv("MQ_GEMM_1CTA");
+  if (M > BM && !(one_env && atoi(one_env))) {
+    const int rc = launch_w4a8_gemm_2cta(tmap, p, (cudaStream_t)stream);
+    if (rc != MQ_OK) return rc;
+    MQ_LAUNCH_CHECK("w4a8_gemm_2cta_kernel");
+    return MQ_OK;
+  }
   MQ_CUDA(cudaFuncSetAttribute(w4a8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
