@@ -91,16 +91,16 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1 + NUM_CONV);
+      mbar_init(full_bar(s), 1 + NUM_CONV / 32);  // TMA thread + one arrive per converter warp
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < WSTAGES; ++s) {
       mbar_init(wfull_bar(s), 1);
-      mbar_init(wempty_bar(s), NUM_CONV);
+      mbar_init(wempty_bar(s), NUM_CONV / 32);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -213,8 +213,11 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
         for (int j = 0; j < 4; ++j) unpack_store(brow, rsw, j, pk[j]);
       }
       fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(full_bar(stage));
-      if (do_w) mbar_arrive(wempty_bar(ws));  // the loads above have been consumed by the stores
+      __syncwarp();        // ... and ordered before lane 0's release-arrive (one arrival per warp)
+      if (lane == 0) {
+        mbar_arrive(full_bar(stage));
+        if (do_w) mbar_arrive(wempty_bar(ws));  // the loads above have been consumed by the stores
+      }
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       if (++ws == WSTAGES) { ws = 0; wphase ^= 1u; }
     }
@@ -273,7 +276,8 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
 
@@ -331,9 +335,10 @@ extern "C" int mq_w4a8_gemm(const int8_t* qa, int64_t lda, const uint8_t* w4, co
   p.k_tiles = (int)(K / BK);
   const char* dbg_env = getenv("MQ_GEMM_DEBUG");
   p.dbg = dbg_env ? (unsigned)atoi(dbg_env) : 0u;
-  // M > 128: CTA pairs (cta_group::2, 256 x 256 tiles); small M keeps the 1-CTA kernel
-  const char* one_env = getenv("MQ_GEMM_1CTA");
-  if (M > BM && !(one_env && atoi(one_env))) {
+  // The cta_group::2 kernel (256 x 256 tile per CTA pair) is correct but currently slower than this
+  // one (its TMA path under-performs, profiles/README.md); it is opt-in until that is resolved.
+  const char* two_env = getenv("MQ_GEMM_2CTA");
+  if (M > BM && two_env && atoi(two_env)) {
     const int rc = launch_w4a8_gemm_2cta(tmap, p, (cudaStream_t)stream);
     if (rc != MQ_OK) return rc;
     MQ_LAUNCH_CHECK("w4a8_gemm_2cta_kernel");

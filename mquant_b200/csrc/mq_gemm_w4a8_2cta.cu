@@ -35,16 +35,17 @@ constexpr int A_STAGE = BM * BK;        // 16 KB
 constexpr int B_STAGE = BNH * BK;       // 16 KB
 constexpr int W_STAGE = BNH * BK / 2;   // 8 KB = 4 runs of 2 KB out of the 256-row blob
 constexpr int NUM_THREADS = 512;
-constexpr int EPI_WARP0 = 4;
-constexpr int CONV_WARP0 = 8;
-constexpr int NUM_CONV = 256;
+constexpr int EPI_WARP0 = 4;     // 8 epilogue warps: lane quadrant = warp & 3, column half = (warp - 4) >> 2
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int CONV_WARP0 = 12;   // 4 converter warps: one full 128-byte row of the B half per thread
+constexpr int NUM_CONV = 128;
 constexpr int TMEM_COLS = 512;
 
 constexpr int SM_A = 0;
 constexpr int SM_B = SM_A + STAGES * A_STAGE;
 constexpr int SM_W = SM_B + STAGES * B_STAGE;
-constexpr int SM_EPI = SM_W + WSTAGES * W_STAGE;      // 4 warps x 32 rows x 128 B
-constexpr int SM_PARAM = SM_EPI + 4 * 4096;           // 2 x {s_w16[256], bias[256], w0[256]} fp32
+constexpr int SM_EPI = SM_W + WSTAGES * W_STAGE;      // 8 warps x 32 rows x 64 B
+constexpr int SM_PARAM = SM_EPI + NUM_EPI_WARPS * 2048;  // 2 x {s_w16[256], bias[256], w0[256]} fp32
 constexpr int SM_BAR = SM_PARAM + 2 * 3 * BN * 4;
 constexpr int SM_TMEMPTR = SM_BAR + (2 * STAGES + 2 * WSTAGES + 4) * 8;
 constexpr int SM_TOTAL = SM_TMEMPTR + 16;
@@ -70,12 +71,24 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+// NOTE: waits use the plain CTA-scope mbarrier.try_wait (as CUTLASS's ClusterBarrier does): an
+// acquire.cluster wait compiles to TRYWAIT + CCTL.IVALL (L1 invalidate) and, executed once per
+// k-block by the MMA warp, halved the kernel's throughput (profiles/README.md).  The data the
+// waits guard is written through the async proxy (TMA) or published with fence.proxy.async +
+// release.cluster arrives, and consumed by the tensor core after tcgen05.fence::after_thread_sync.
+// dbg bit 32 selects a pure polling wait (mbarrier.test_wait) instead of the suspending try_wait:
+// used to test whether arrivals that come from the OTHER CTA (relay arrive, multicast commit)
+// wake a suspended try_wait promptly.
+__device__ __forceinline__ void mbar_wait2(uint32_t bar, uint32_t parity, bool spin) {
+  if (!spin) {
+    mbar_wait(bar, parity);
+    return;
+  }
   uint32_t done;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)
@@ -106,6 +119,19 @@ __device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+      "%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 w4a8_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -128,20 +154,26 @@ w4a8_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int total_tiles = p.m_tiles * p.n_tiles;  // m_tiles counts 256-row tiles here
+  const bool spin = (p.dbg & 32u) != 0;
+  // tile -> (m-block, n-block).  dbg bit 64: m-fastest order (experiment)
+  const bool mfast = (p.dbg & 64u) != 0;
+  auto tile_mb = [&](int t) { return mfast ? (t % p.m_tiles) : (t / p.n_tiles); };
+  auto tile_nb = [&](int t) { return mfast ? (t / p.m_tiles) : (t % p.n_tiles); };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1 + 2 * NUM_CONV);  // used in the leader only
+      // leader: own TMA thread + own converter warps + the peer's relay; peer: TMA thread + converter warps
+      mbar_init(full_bar(s), 1 + NUM_CONV / 32 + (cta == 0 ? 1 : 0));
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < WSTAGES; ++s) {
       mbar_init(wfull_bar(s), 1);
-      mbar_init(wempty_bar(s), NUM_CONV);
+      mbar_init(wempty_bar(s), NUM_CONV / 32);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 2 * 128);  // used in the leader only
+      mbar_init(tempty_bar(a), 2 * NUM_EPI_WARPS);  // leader only: one arrive per epilogue warp of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -158,20 +190,21 @@ w4a8_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer (A): 128 rows per CTA, tx bytes land on the leader's barrier
+    // ===================== TMA producer (A): 128 rows per CTA, completing on the CTA's OWN barrier.
+    // (A first version used the .cta_group::2 TMA form with the leader's barrier as the remote
+    // complete_tx target: TMA throughput dropped 2.6x, profiles/r1_gemm_probes_2cta.log.)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < total_tiles; t += num_pairs) {
-        const int mb = t / p.n_tiles;
+        const int mb = tile_mb(t);
         for (int kb = 0; kb < p.k_tiles; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_wait2(empty_bar(stage), phase ^ 1u, spin);
           if (p.dbg & 2u) {
-            if (cta == 0) mbar_arrive(full_bar(stage));
+            mbar_arrive(full_bar(stage));
           } else {
-            if (cta == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * A_STAGE);
-            tma_load_2d_2cta(sA + stage * A_STAGE, &tmap_a, kb * BK, mb * (2 * BM) + (int)cta * BM,
-                             mapa(full_bar(stage), 0));
+            mbar_arrive_expect_tx(full_bar(stage), A_STAGE);
+            tma_load_2d(sA + stage * A_STAGE, &tmap_a, kb * BK, mb * (2 * BM) + (int)cta * BM, full_bar(stage));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -183,9 +216,9 @@ w4a8_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p
       int ws = 0;
       uint32_t wphase = 0;
       for (int t = pair; t < total_tiles; t += num_pairs) {
-        const int nb = t % p.n_tiles;
+        const int nb = tile_nb(t);
         for (int kb = 0; kb < p.k_tiles; ++kb) {
-          mbar_wait(wempty_bar(ws), wphase ^ 1u);
+          mbar_wait2(wempty_bar(ws), wphase ^ 1u, spin);
           mbar_arrive_expect_tx(wfull_bar(ws), W_STAGE);
           const uint8_t* blob = p.w4 + w4_blob_offset(nb, kb, p.k_tiles) + (size_t)cta * (BNH * 16);
 #pragma unroll
@@ -197,19 +230,33 @@ w4a8_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (cta == 0) {
+    // ===================== MMA issuer (leader) / readiness relay (peer) =====================
+    if (cta != 0) {
+      // the peer's operands are ready when ITS full barrier completes (own TMA bytes + own
+      // converter warps); forward that to the leader with ONE remote arrive per k-block
+      const uint32_t full_leader = mapa(bar0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < total_tiles; t += num_pairs) {
+        for (int kb = 0; kb < p.k_tiles; ++kb) {
+          mbar_wait2(full_bar(stage), phase, spin);
+          if (lane == 0) mbar_arrive_cluster(full_leader + 8u * stage);
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
       for (int t = pair; t < total_tiles; t += num_pairs, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
-        mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait2(tempty_bar(acc), acc_phase ^ 1u, spin);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.k_tiles; ++kb) {
-          mbar_wait_cluster(full_bar(stage), phase);
+          mbar_wait2(full_bar(stage), phase, spin);
           tc_fence_after();
           if (lane == 0) {
             const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * A_STAGE);
@@ -228,13 +275,10 @@ w4a8_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p
       }
     }
   } else if (warp >= CONV_WARP0) {
-    // ===================== weight converters: 256 threads, (row, half of the k-block) each
-    const int ct = threadIdx.x - CONV_WARP0 * 32;
-    const int r = ct & (BNH - 1);  // row of this CTA's 128-row B half
-    const int h = ct >> 7;         // 0: k 0..63, 1: k 64..127 (warp uniform)
+    // ===================== weight converters: 128 threads, one 128-byte row of the B half each
+    const int r = threadIdx.x - CONV_WARP0 * 32;
     const int rsw = r & 7;
     const uint32_t brow_off = (uint32_t)r * 128u;
-    const uint32_t full_leader = mapa(bar0, 0);  // leader's barrier block (same offsets)
     const int my_tiles = (total_tiles - pair + num_pairs - 1) / num_pairs;
     const int total_it = my_tiles * p.k_tiles;
     const bool do_w = !(p.dbg & 1u);
@@ -242,51 +286,57 @@ w4a8_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p
     int stage = 0, ws = 0;
     uint32_t phase = 0, wphase = 0;
     for (int it = 0; it < total_it; ++it) {
-      uint4 pk[2];
+      uint4 pk[4];
       if (do_w) {
-        mbar_wait(wfull_bar(ws), wphase);
-        const uint32_t src = sW + ws * W_STAGE + (uint32_t)(2 * h) * (BNH * 16) + (uint32_t)r * 16u;
+        mbar_wait2(wfull_bar(ws), wphase, spin);
+        const uint32_t src = sW + ws * W_STAGE + (uint32_t)r * 16u;
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
+        for (int j = 0; j < 4; ++j) {
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(pk[jj].x), "=r"(pk[jj].y), "=r"(pk[jj].z), "=r"(pk[jj].w)
-                       : "r"(src + (uint32_t)jj * (BNH * 16)));
+                       : "=r"(pk[j].x), "=r"(pk[j].y), "=r"(pk[j].z), "=r"(pk[j].w)
+                       : "r"(src + (uint32_t)j * (BNH * 16)));
         }
       }
-      mbar_wait(empty_bar(stage), phase ^ 1u);
+      mbar_wait2(empty_bar(stage), phase ^ 1u, spin);
       const uint32_t brow = sB + stage * B_STAGE + brow_off;
       if (do_sts) {
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) unpack_store(brow, rsw, 2 * h + jj, pk[jj]);
+        for (int j = 0; j < 4; ++j) unpack_store(brow, rsw, j, pk[j]);
       }
       fence_async_smem();
-      if (cta == 0) mbar_arrive(full_bar(stage));
-      else mbar_arrive_cluster(full_leader + 8u * stage);
-      if (do_w) mbar_arrive(wempty_bar(ws));
+      // one arrival per warp on the CTA's own barrier; __syncwarp orders the lanes' (already
+      // proxy-fenced) stores before lane 0's release-arrive
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(full_bar(stage));
+        if (do_w) mbar_arrive(wempty_bar(ws));
+      }
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       if (++ws == WSTAGES) { ws = 0; wphase ^= 1u; }
     }
   } else if (warp >= EPI_WARP0) {
-    // ===================== epilogue =====================
+    // ===================== epilogue: 8 warps = 4 lane quadrants x 2 column halves ===============
     const int quad = warp & 3;
-    const int et = threadIdx.x - EPI_WARP0 * 32;
+    const int chalf = (warp - EPI_WARP0) >> 2;
+    const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
     float* params = reinterpret_cast<float*>(smem + SM_PARAM);
-    const uint32_t stg = base + SM_EPI + quad * 4096;
+    const uint32_t stg = base + SM_EPI + (uint32_t)(warp - EPI_WARP0) * 2048u;
     const uint32_t tempty_leader = mapa(tempty_bar(0), 0);
     int local = 0;
     for (int t = pair; t < total_tiles; t += num_pairs, ++local) {
-      const int mb = t / p.n_tiles, nb = t % p.n_tiles;
+      const int mb = tile_mb(t), nb = tile_nb(t);
       const int acc = local & 1;
       const uint32_t acc_phase = (uint32_t)(local >> 1) & 1u;
       float* ps = params + acc * 3 * BN;
-      for (int c = et; c < BN; c += 128) {
+      {
+        const int c = et;
         const int n = nb * BN + c;
         const bool ok = n < p.N;
-        ps[c] = ok ? __fmul_rn(p.s_w[n], 0.0625f) : 0.f;
+        ps[c] = ok ? __fmul_rn(p.s_w[n], 0.0625f) : 0.f;  // the INT8 operand holds 16 x code
         ps[BN + c] = (ok && p.bias != nullptr) ? __half2float(p.bias[n]) : 0.f;
         ps[2 * BN + c] = (ok && p.w0 != nullptr) ? __half2float(p.w0[n]) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const int m_warp0 = mb * (2 * BM) + (int)cta * BM + quad * 32;
       const int m = m_warp0 + lane;
       float sa = 0.f, x0v = 0.f;
@@ -295,51 +345,62 @@ w4a8_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p
         if (p.x0 != nullptr) x0v = __half2float(p.x0[m]);
       }
       const bool has_r1 = p.x0 != nullptr, has_bias = p.bias != nullptr;
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait2(tfull_bar(acc), acc_phase, spin);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c2 = 0; c2 < BN / 64; ++c2) {
+      const int col0 = chalf * (BN / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0);
+      uint32_t va[32], vb[32];
+      tmem_ld32_nowait(taddr, va);
+      auto process = [&](const uint32_t (&v)[32], int cc) {
+        const int colb = col0 + cc * 32;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c2 * 64 + hf * 32, v);
+        for (int g = 0; g < 4; ++g) {
+          const int col = colb + g * 8;
+          float y[8];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = c2 * 64 + hf * 32 + g * 8;
-            float y[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float sc = __fmul_rn(sa, ps[col + e]);
-              float val = __fmul_rn((float)(int)v[g * 8 + e], sc);
-              if (has_r1) val = __fadd_rn(val, __fmul_rn(x0v, ps[2 * BN + col + e]));
-              if (has_bias) val = __fadd_rn(val, ps[BN + col + e]);
-              y[e] = val;
-            }
-            const uint4 hv = pack8_f16(y);
-            const uint32_t dst = stg + lane * 128 + ((uint32_t)((hf * 4 + g) ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w) : "memory");
+          for (int e = 0; e < 8; ++e) {
+            const float sc = __fmul_rn(sa, ps[col + e]);
+            float val = __fmul_rn((float)(int)v[g * 8 + e], sc);
+            if (has_r1) val = __fadd_rn(val, __fmul_rn(x0v, ps[2 * BN + col + e]));
+            if (has_bias) val = __fadd_rn(val, ps[BN + col + e]);
+            y[e] = val;
           }
+          const uint4 hv = pack8_f16(y);
+          // per-warp staging: 32 rows x 64 B, 16-byte chunk g of row `lane` at (g ^ (lane>>1)&3)
+          const uint32_t dst = stg + lane * 64 + ((uint32_t)(g ^ ((lane >> 1) & 3)) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w) : "memory");
         }
         __syncwarp();
-        // 8 lanes cover one row's 128 bytes: 4 rows per instruction, full 128-byte lines
-        const int ch = lane & 7;
-        const int ncol = nb * BN + c2 * 64 + ch * 8;
+        // 4 lanes cover one row's 64 bytes: 8 rows per instruction, whole 32-byte sectors
+        const int ch = lane & 3;
+        const int ncol = nb * BN + colb + ch * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 4 + (lane >> 3);
+        for (int i = 0; i < 4; ++i) {
+          const int row = i * 8 + (lane >> 2);
           uint4 hv;
-          const uint32_t src = stg + row * 128 + ((uint32_t)(ch ^ (row & 7)) << 4);
+          const uint32_t src = stg + row * 64 + ((uint32_t)(ch ^ ((row >> 1) & 3)) << 4);
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hv.x), "=r"(hv.y), "=r"(hv.z), "=r"(hv.w) : "r"(src));
           const int mr = m_warp0 + row;
-          if (mr < p.M && ncol < p.N && !(p.dbg & 4u))
-            stg_stream(p.out + (int64_t)mr * p.ldo + ncol, hv);
+          if (mr < p.M && ncol < p.N && !(p.dbg & 4u)) stg_stream(p.out + (int64_t)mr * p.ldo + ncol, hv);
         }
         __syncwarp();
+      };
+      // TMEM loads are software pipelined: the load of chunk c+1 is in flight while c is processed
+#pragma unroll 1
+      for (int cc = 0; cc < (BN / 2) / 32; cc += 2) {
+        tmem_wait_ld();
+        tmem_ld32_nowait(taddr + (cc + 1) * 32, vb);
+        process(va, cc);
+        tmem_wait_ld();
+        if (cc + 2 < (BN / 2) / 32) tmem_ld32_nowait(taddr + (cc + 2) * 32, va);
+        process(vb, cc + 1);
       }
       tc_fence_before();
-      if (cta == 0) mbar_arrive(tempty_bar(acc));
-      else mbar_arrive_cluster(tempty_leader + 8u * acc);
+      __syncwarp();
+      if (lane == 0) {
+        if (cta == 0) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cluster(tempty_leader + 8u * acc);
+      }
     }
   }
 
@@ -359,10 +420,7 @@ int launch_w4a8_gemm_2cta(const CUtensorMap& tmap_a, const Params& p_in, cudaStr
   p.m_tiles = (p.M + 2 * BM - 1) / (2 * BM);  // 256-row tiles
   MQ_CUDA(cudaFuncSetAttribute(w4a8_gemm_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
-  const int max_pairs = num_sms() / 2;
-  const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SM_ALLOC;
   cfg.stream = st;
@@ -373,6 +431,20 @@ int launch_w4a8_gemm_2cta(const CUtensorMap& tmap_a, const Params& p_in, cudaStr
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // A persistent kernel must not launch more clusters than can be co-resident: the surplus would
+  // run as a second wave after the first one finishes (static tile assignment => 2x time).  Not
+  // every TPC can host a 2-CTA cluster of this size, so ask the runtime.
+  static int max_pairs_cached = 0;
+  if (max_pairs_cached == 0) {
+    cfg.gridDim = dim3(num_sms());
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, w4a8_gemm_2cta_kernel, &cfg) != cudaSuccess || n <= 0) n = num_sms() / 2;
+    max_pairs_cached = n;
+    if (p.dbg & 128u) fprintf(stderr, "mq_w4a8_gemm: max co-resident CTA pairs = %d (SMs %d)\n", n, num_sms());
+  }
+  const int max_pairs = max_pairs_cached;
+  const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
+  cfg.gridDim = dim3(2 * pairs);
   MQ_CUDA(cudaLaunchKernelEx(&cfg, w4a8_gemm_2cta_kernel, tmap_a, p));
   return MQ_OK;
 }
