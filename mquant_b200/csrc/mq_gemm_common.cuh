@@ -50,8 +50,9 @@ __device__ __forceinline__ void unpack_store(uint32_t brow, int rsw, int j, cons
 }
 
 
-// mq_gemm_w4a8_2cta.cu: cta_group::2 kernel (256 x 256 tile per CTA pair)
-int launch_w4a8_gemm_2cta(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st);
+// mq_gemm_w4a8_v2.cu: second-generation kernel; two_cta selects the cta_group::2 flavour
+// (256 x 256 tile per CTA pair)
+int launch_w4a8_gemm_v2(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st, bool two_cta);
 
 }  // namespace gemm
 }  // namespace mq

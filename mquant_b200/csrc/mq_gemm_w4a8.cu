@@ -335,13 +335,16 @@ extern "C" int mq_w4a8_gemm(const int8_t* qa, int64_t lda, const uint8_t* w4, co
   p.k_tiles = (int)(K / BK);
   const char* dbg_env = getenv("MQ_GEMM_DEBUG");
   p.dbg = dbg_env ? (unsigned)atoi(dbg_env) : 0u;
-  // The cta_group::2 kernel (256 x 256 tile per CTA pair) is correct but currently slower than this
-  // one (its TMA path under-performs, profiles/README.md); it is opt-in until that is resolved.
-  const char* two_env = getenv("MQ_GEMM_2CTA");
-  if (M > BM && two_env && atoi(two_env)) {
-    const int rc = launch_w4a8_gemm_2cta(tmap, p, (cudaStream_t)stream);
+  // Kernel selection (MQ_GEMM_KERNEL = v1 | v2 | 2cta overrides): v2 = 8-warp pipelined epilogue
+  // with staged stores; 2cta = its cta_group::2 flavour (correct, but its TMA path currently
+  // under-performs, profiles/README.md); v1 = this file's first-generation kernel.
+  const char* kenv = getenv("MQ_GEMM_KERNEL");
+  int kernel = 2;  // default: v2
+  if (kenv) kernel = (kenv[0] == '2') ? 3 : (kenv[0] == 'v' && kenv[1] == '1') ? 1 : 2;
+  if (kernel >= 2) {
+    const int rc = launch_w4a8_gemm_v2(tmap, p, (cudaStream_t)stream, kernel == 3 && M > BM);
     if (rc != MQ_OK) return rc;
-    MQ_LAUNCH_CHECK("w4a8_gemm_2cta_kernel");
+    MQ_LAUNCH_CHECK("w4a8_gemm_v2_kernel");
     return MQ_OK;
   }
   MQ_CUDA(cudaFuncSetAttribute(w4a8_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
