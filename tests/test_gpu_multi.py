@@ -22,8 +22,18 @@ def _make_model(device):
     from mquant_b200 import quant_utils as qu
 
     torch.manual_seed(0)
-    m = torch.nn.Sequential(torch.nn.Linear(256, 512, bias=False), torch.nn.Linear(512, 256, bias=False)).half().to(device)
+
+    class Net(torch.nn.Module):  # add_actquant wraps Linear ATTRIBUTES / Sequential members of a parent
+        def __init__(self):
+            super().__init__()
+            self.seq = torch.nn.Sequential(torch.nn.Linear(256, 512, bias=False), torch.nn.Linear(512, 256, bias=False))
+
+        def forward(self, x):
+            return self.seq(x)
+
+    m = Net().half().to(device)
     qu.add_actquant(m)
+    assert len(qu.find_qlayers(m, layers=[qu.ActQuantWrapper])) == 2
     for l in qu.find_qlayers(m, layers=[qu.ActQuantWrapper]).values():
         l.quantizer.configure(bits=8, sym=True, static=True, observer_type="minmax")
     return m
