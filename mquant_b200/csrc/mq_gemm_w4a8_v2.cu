@@ -108,19 +108,6 @@ __device__ __forceinline__ void umma_commit_v2(uint32_t bar) {
     umma_commit(bar);
   }
 }
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
-      "%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 template <bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 w4a8_gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
@@ -430,6 +417,16 @@ int launch_w4a8_gemm_v2(const CUtensorMap& tmap_a, const Params& p_in, cudaStrea
                                  Cfg<false>::SM_ALLOC));
     cfg.dynamicSmemBytes = Cfg<false>::SM_ALLOC;
     cfg.gridDim = dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()));
+    cudaLaunchAttribute cattr[1];
+    if (p.dbg & 256u) {  // experiment: same kernel, launched as clusters of 2 (grid rounded to even)
+      cattr[0].id = cudaLaunchAttributeClusterDimension;
+      cattr[0].val.clusterDim.x = 2;
+      cattr[0].val.clusterDim.y = 1;
+      cattr[0].val.clusterDim.z = 1;
+      cfg.attrs = cattr;
+      cfg.numAttrs = 1;
+      cfg.gridDim = dim3((cfg.gridDim.x + 1) & ~1u);
+    }
     MQ_CUDA(cudaLaunchKernelEx(&cfg, w4a8_gemm_v2_kernel<false>, tmap_a, p));
     return MQ_OK;
   }

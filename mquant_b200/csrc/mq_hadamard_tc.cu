@@ -94,11 +94,11 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(d1_full(s), 1);
-      mbar_init(d1_empty(s), NUM_MID);
-      mbar_init(t_full(s), NUM_MID * rtu);
+      mbar_init(d1_empty(s), NUM_MID / 32);
+      mbar_init(t_full(s), (NUM_MID / 32) * rtu);
       mbar_init(t_empty(s), 1);
       mbar_init(d2_full(s), 1);
-      mbar_init(d2_empty(s), NUM_EPI);
+      mbar_init(d2_empty(s), NUM_EPI / 32);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -219,10 +219,19 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue: D2 -> fp16 -> INT8 codes -> HBM =====================
+    // Thread = one j' (TMEM lane), 16 consecutive k' per chunk.  The 16 codes of a thread belong to
+    // 16 different output rows (stride P), so groups of 4 lanes transpose their 4x4 byte blocks
+    // with two shuffle+PRMT steps and every lane then stores 32-bit words (4 consecutive j' of one
+    // k'): 4 STG.32 per chunk instead of 16 byte stores.  TMEM loads are double buffered.
     const int quad = warp & 3, grp = (warp - EPI_WARP0) >> 2;  // lane quadrant, column-chunk parity
     const int mrow = quad * 32 + lane;                         // D2 lane = (segment, j' within segment)
     const int seg = mrow >> 6, jl = mrow & 63;
     const int chunks = c.Kpad / 16;
+    const int la = lane & 3;
+    const uint32_t sel1 = (la & 1) ? 0x3715u : 0x6240u;  // 4x4 byte transpose, step xor-1
+    const uint32_t sel2 = (la & 2) ? 0x3276u : 0x5410u;  // ... step xor-2
+    const QScale q_text = make_qscale(__ldg(a.scales)), q_vis = make_qscale(__ldg(a.scales + 1));
+    const bool split = (a.flags & MQ_FLAG_SPLIT) != 0;
     int lu = 0;
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++lu) {
       const int d2 = lu & 1;
@@ -230,42 +239,60 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       const int64_t tok = (S == 1) ? (u * TPU + seg) : u;
       const int j = (S == 1) ? jl : (seg * 64 + jl);
       const bool live = tok < a.M;
-      float s_act = 1.f;
-      if (live) s_act = (a.modality != nullptr && a.modality[tok] != 0) ? __ldg(a.scales + 1) : __ldg(a.scales);
-      const QScale qs = make_qscale(s_act);
-      if (live && j == 0 && grp == 0 && a.srow_out != nullptr) a.srow_out[tok] = s_act;
+      const bool vis = live && a.modality != nullptr && a.modality[tok] != 0;
+      QScale qs;  // field-wise select keeps it in registers
+      qs.s = vis ? q_vis.s : q_text.s;
+      qs.inv_lo = vis ? q_vis.inv_lo : q_text.inv_lo;
+      qs.inv_hi = vis ? q_vis.inv_hi : q_text.inv_hi;
+      qs.lim_lo = vis ? q_vis.lim_lo : q_text.lim_lo;
+      qs.lim_hi = vis ? q_vis.lim_hi : q_text.lim_hi;
+      if (live && j == 0 && grp == 0 && a.srow_out != nullptr) a.srow_out[tok] = qs.s;
       mbar_wait(d2_full(d2), d2ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(d2 ? D2_COL1 : D2_COL0);
-      int8_t* orow = a.q + tok * (int64_t)a.n + j;
-      for (int ch = grp; ch < chunks; ch += 2) {
-        uint32_t v[16];
-        tmem_ld16(taddr + ch * 16, v);
-        if (live) {
+      int8_t* obase = a.q + tok * (int64_t)a.n + (j - la);  // word-aligned: 4 consecutive j' per store
+      auto process = [&](const uint32_t (&v)[16], int ch) {
+        uint32_t w[4];
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            float f[8];
+        for (int g = 0; g < 2; ++g) {
+          float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
-            const uint4 h = pack8_f16(f);  // second rounding point (hadK @ . -> fp16)
-            uint2 r = quant8(h, qs);
-            const int k0 = ch * 16 + g * 8;
-            if (k0 == 0 && j == 0 && (a.flags & MQ_FLAG_SPLIT)) {
-              a.x0_out[tok] = reinterpret_cast<const __half*>(&h)[0];
-              r.x &= 0xffffff00u;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if (k0 + e < c.had_k) {
-                const uint32_t w = e < 4 ? r.x : r.y;
-                orow[(int64_t)(k0 + e) * P] = (int8_t)((w >> (8 * (e & 3))) & 0xff);
-              }
-            }
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+          const uint4 h = pack8_f16(f);  // second rounding point (hadK @ . -> fp16)
+          uint2 r = quant8(h, qs);
+          if (split && ch == 0 && g == 0 && j == 0) {
+            if (live) a.x0_out[tok] = reinterpret_cast<const __half*>(&h)[0];
+            r.x &= 0xffffff00u;
           }
+          w[2 * g] = r.x;
+          w[2 * g + 1] = r.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t t1 = __shfl_xor_sync(0xffffffffu, w[i], 1);
+          uint32_t x1 = __byte_perm(w[i], t1, sel1);
+          uint32_t t2 = __shfl_xor_sync(0xffffffffu, x1, 2);
+          const uint32_t x2 = __byte_perm(x1, t2, sel2);  // codes of k' = 16ch + 4i + la, j' = 4*(lane/4) .. +3
+          const int kp = ch * 16 + 4 * i + la;
+          if (live && kp < c.had_k) *reinterpret_cast<uint32_t*>(obase + (int64_t)kp * P) = x2;
+        }
+      };
+      uint32_t va[16], vb[16];
+      int ch = grp;
+      if (ch < chunks) tmem_ld16_nowait(taddr + ch * 16, va);
+      for (; ch < chunks; ch += 4) {
+        tmem_wait_ld();
+        if (ch + 2 < chunks) tmem_ld16_nowait(taddr + (ch + 2) * 16, vb);
+        process(va, ch);
+        if (ch + 2 < chunks) {
+          tmem_wait_ld();
+          if (ch + 4 < chunks) tmem_ld16_nowait(taddr + (ch + 4) * 16, va);
+          process(vb, ch + 2);
         }
       }
       tc_fence_before();
-      mbar_arrive(d2_empty(d2));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d2_empty(d2));
     }
   } else if (warp >= MID_WARP0) {
     // ===================== mid stage: D1 -> * norm -> fp16 -> T (MN-major A of MMA2) =============
@@ -283,10 +310,7 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
           mbar_wait(d1_full(d1), d1ph);
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL + d1 * P);
-#pragma unroll
-          for (int cb = 0; cb < P / 32; ++cb) {
-            uint32_t v[32];
-            tmem_ld32(taddr + cb * 32, v);
+          auto convert = [&](const uint32_t (&v)[32], int cb) {
             if (k < c.Kpad) {
               // segment of these 32 j' values; T[(seg), k, j' % 64]
               const int sgi = tk * S + (cb * 32) / 64;
@@ -302,11 +326,26 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
                 asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w) : "memory");
               }
             }
+          };
+          // TMEM loads double buffered against the conversion
+          uint32_t va[32], vb[32];
+          tmem_ld32_nowait(taddr, va);
+#pragma unroll
+          for (int cb = 0; cb < P / 32; cb += 2) {
+            tmem_wait_ld();
+            tmem_ld32_nowait(taddr + (cb + 1) * 32, vb);
+            convert(va, cb);
+            tmem_wait_ld();
+            if (cb + 2 < P / 32) tmem_ld32_nowait(taddr + (cb + 2) * 32, va);
+            convert(vb, cb + 1);
           }
           tc_fence_before();
-          mbar_arrive(d1_empty(d1));
           fence_async_smem();
-          mbar_arrive(t_full(tb));
+          __syncwarp();  // one arrival per warp on each barrier
+          if (lane == 0) {
+            mbar_arrive(d1_empty(d1));
+            mbar_arrive(t_full(tb));
+          }
           if (++d1 == D1B) { d1 = 0; d1ph ^= 1u; }
         }
       }
