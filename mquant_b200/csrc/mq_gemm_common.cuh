@@ -53,6 +53,8 @@ __device__ __forceinline__ void unpack_store(uint32_t brow, int rsw, int j, cons
 // mq_gemm_w4a8_v2.cu: second-generation kernel; two_cta selects the cta_group::2 flavour
 // (256 x 256 tile per CTA pair)
 int launch_w4a8_gemm_v2(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st, bool two_cta);
+// mq_gemm_w4a8_v3.cu: register-path weights (no staging ring), two alternating converter groups
+int launch_w4a8_gemm_v3(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st);
 
 }  // namespace gemm
 }  // namespace mq

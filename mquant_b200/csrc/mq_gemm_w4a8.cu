@@ -339,8 +339,19 @@ extern "C" int mq_w4a8_gemm(const int8_t* qa, int64_t lda, const uint8_t* w4, co
   // with staged stores; 2cta = its cta_group::2 flavour (correct, but its TMA path currently
   // under-performs, profiles/README.md); v1 = this file's first-generation kernel.
   const char* kenv = getenv("MQ_GEMM_KERNEL");
-  int kernel = 2;  // default: v2
-  if (kenv) kernel = (kenv[0] == '2') ? 3 : (kenv[0] == 'v' && kenv[1] == '1') ? 1 : 2;
+  int kernel = 2;  // default
+  if (kenv) {
+    if (kenv[0] == '2') kernel = 3;                         // "2cta"
+    else if (kenv[0] == 'v' && kenv[1] == '1') kernel = 1;  // "v1"
+    else if (kenv[0] == 'v' && kenv[1] == '3') kernel = 4;  // "v3"
+    else kernel = 2;                                        // "v2"
+  }
+  if (kernel == 4) {
+    const int rc = launch_w4a8_gemm_v3(tmap, p, (cudaStream_t)stream);
+    if (rc != MQ_OK) return rc;
+    MQ_LAUNCH_CHECK("w4a8_gemm_v3_kernel");
+    return MQ_OK;
+  }
   if (kernel >= 2) {
     const int rc = launch_w4a8_gemm_v2(tmap, p, (cudaStream_t)stream, kernel == 3 && M > BM);
     if (rc != MQ_OK) return rc;

@@ -265,41 +265,62 @@ w4a8_gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) 
     const bool do_sts = !(p.dbg & (1u | 16u));
     int stage = 0, ws = 0;
     uint32_t phase = 0, wphase = 0;
-    for (int it = 0; it < total_it; ++it) {
-      uint4 pk[C::ROWS][4];
-      if (do_w) {
-        mbar_wait(wfull_bar(ws), wphase);
+    // Software pipelined: the staging reads of k-block it+1 are issued BEFORE the proxy fence of
+    // k-block it (the fence is a MEMBAR: it would otherwise serialise LDS latency + STS drain of
+    // consecutive k-blocks, and the converters' per-k-block latency exceeded the 512-cycle MMA time).
+    uint4 pk[2][C::ROWS][4];
+    auto load_pk = [&](uint4 (&dst)[C::ROWS][4], int slot) {
 #pragma unroll
-        for (int rr = 0; rr < C::ROWS; ++rr) {
-          const uint32_t src = sW + ws * C::W_STAGE + (uint32_t)(r0 + rr * NUM_CONV) * 16u;
+      for (int rr = 0; rr < C::ROWS; ++rr) {
+        const uint32_t src = sW + slot * C::W_STAGE + (uint32_t)(r0 + rr * NUM_CONV) * 16u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(pk[rr][j].x), "=r"(pk[rr][j].y), "=r"(pk[rr][j].z), "=r"(pk[rr][j].w)
-                         : "r"(src + (uint32_t)j * (C::BNH * 16)));
+        for (int j = 0; j < 4; ++j) {
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(dst[rr][j].x), "=r"(dst[rr][j].y), "=r"(dst[rr][j].z), "=r"(dst[rr][j].w)
+                       : "r"(src + (uint32_t)j * (C::BNH * 16)));
+        }
+      }
+    };
+    auto store_pk = [&](const uint4 (&src)[C::ROWS][4], int st) {
+#pragma unroll
+      for (int rr = 0; rr < C::ROWS; ++rr) {
+        const int r = r0 + rr * NUM_CONV;
+        const uint32_t brow = sB + st * C::B_STAGE + (uint32_t)r * 128u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) unpack_store(brow, r & 7, j, src[rr][j]);
+      }
+    };
+    if (do_w && total_it > 0) {
+      mbar_wait(wfull_bar(0), 0);
+      load_pk(pk[0], 0);
+    }
+    for (int it = 0; it < total_it; it += 2) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (it + half < total_it) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (do_sts) store_pk(pk[half], stage);
+          // prefetch the next k-block's packed weights into the other register set
+          int ws_next = ws + 1;
+          uint32_t wphase_next = wphase;
+          if (ws_next == WSTAGES) { ws_next = 0; wphase_next ^= 1u; }
+          if (do_w && it + half + 1 < total_it) {
+            mbar_wait(wfull_bar(ws_next), wphase_next);
+            load_pk(pk[half ^ 1], ws_next);
           }
+          fence_async_smem();
+          // one arrival per warp; __syncwarp orders the lanes' (already proxy-fenced) stores before
+          // lane 0's release-arrive
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(full_bar(stage));
+            if (do_w) mbar_arrive(wempty_bar(ws));  // slot `ws` was consumed by the stores above
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          ws = ws_next;
+          wphase = wphase_next;
         }
       }
-      mbar_wait(empty_bar(stage), phase ^ 1u);
-      if (do_sts) {
-#pragma unroll
-        for (int rr = 0; rr < C::ROWS; ++rr) {
-          const int r = r0 + rr * NUM_CONV;
-          const uint32_t brow = sB + stage * C::B_STAGE + (uint32_t)r * 128u;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) unpack_store(brow, r & 7, j, pk[rr][j]);
-        }
-      }
-      fence_async_smem();
-      // one arrival per warp; __syncwarp orders the lanes' (already proxy-fenced) stores before
-      // lane 0's release-arrive
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(full_bar(stage));
-        if (do_w) mbar_arrive(wempty_bar(ws));
-      }
-      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-      if (++ws == WSTAGES) { ws = 0; wphase ^= 1u; }
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue: 8 warps = 4 lane quadrants x 2 column halves ===============
