@@ -266,8 +266,14 @@ def main():
         peak_src = "2 x measured bf16_tflops_sustained (MEASURED_PEAKS.json; INT8 = 2x bf16 rate, no INT8 entry)"
     else:
         peak, peak_src = 2.0 * 1400.0, "2 x fallback sustained bf16 (B200_PROFILING.md)"
-    roofline = {"bound": "tensor", "kernel": "w4a8_gemm_kernel", "achieved": achieved, "peak": peak,
-                "unit": "TOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per
+    # launch, averaged over the step's shape mix); only meaningful for the default workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1b_gemm_traffic.json")
+    if os.path.exists(tpath) and a.tokens == 16384:
+        traffic = json.load(open(tpath)).get("avg_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "w4a8_gemm_v2_kernel", "achieved": achieved, "peak": peak,
+                "unit": "TOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "peak_nominal": 4500.0, "frac_nominal": achieved / 4500.0,
                 "avg_launch_ms": gemm_total_ms / max(n_gemm, 1), "launches_timed": n_gemm,
                 "share_of_step": gemm_total_ms / ms_step}

@@ -177,6 +177,7 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
           const uint32_t tm = tmem_base + D1_COL + d1 * P;
 #pragma unroll
           for (int k = 0; k < P / 16; ++k) {
+            if (prm.dbg & 16u) break;  // probe: no MMA1
             const uint32_t koff = (uint32_t)(k / 4) * (128 * 128) + (uint32_t)(k % 4) * 32u;
             const uint32_t boff = (uint32_t)(k / 4) * (P * 128) + (uint32_t)(k % 4) * 32u;
             umma_f16(tm, make_sw128_desc(sX + xs * c.x_stage + koff, 0, 1024),
@@ -207,6 +208,7 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
         const uint32_t lbo = (prm.dbg & 1u) ? 1024u : (uint32_t)c.Kpad * 128u;
         const uint32_t sbo = (prm.dbg & 1u) ? (uint32_t)c.Kpad * 128u : 1024u;
         for (int k = 0; k < c.Kpad / 16; ++k) {
+          if (prm.dbg & 8u) break;  // probe: no MMA2
           const uint32_t boff = (uint32_t)(k / 4) * (uint32_t)(c.Kpad * 128) + (uint32_t)(k % 4) * 32u;
           umma_f16(tm, make_sw128_desc(tbase + (uint32_t)k * 2048u, lbo, sbo),
                    make_sw128_desc(sB2 + boff, 0, 1024), idesc2, (uint32_t)(k != 0));
@@ -252,6 +254,7 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(d2 ? D2_COL1 : D2_COL0);
       int8_t* obase = a.q + tok * (int64_t)a.n + (j - la);  // word-aligned: 4 consecutive j' per store
       auto process = [&](const uint32_t (&v)[16], int ch) {
+        if (prm.dbg & 2u) return;  // probe: TMEM loads only
         uint32_t w[4];
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -311,7 +314,7 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D1_COL + d1 * P);
           auto convert = [&](const uint32_t (&v)[32], int cb) {
-            if (k < c.Kpad) {
+            if (k < c.Kpad && !(prm.dbg & 4u)) {
               // segment of these 32 j' values; T[(seg), k, j' % 64]
               const int sgi = tk * S + (cb * 32) / 64;
               const uint32_t trow = sT + tb * c.t_buf + (uint32_t)sgi * (uint32_t)(c.Kpad * 128) + (uint32_t)k * 128u;

@@ -2,18 +2,36 @@
 # ncu evidence for profiles/: launch list of the bench command + full captures of the hot kernels.
 R=${1:-r1}
 mkdir -p gpurun_out
-echo "=== launch list (bench, 2 layers)"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 56 -c 42 --csv \
+echo "=== launch list (bench, 2 layers): our kernels only, warm-up skipped"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none \
+  -k regex:"w4a8_gemm|act_quant_i8_kernel|hadk_tc_kernel" -s 84 -c 28 --csv \
   --log-file gpurun_out/launches_${R}.csv python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_${R}.log 2>&1
-tail -2 gpurun_out/launches_${R}.log | cut -c1-300
-echo "=== full: gemm"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:w4a8_gemm_kernel -s 3 -c 3 -f -o gpurun_out/prof_gemm_${R} python tools/profile_target.py gemm 16384 > gpurun_out/ncu_gemm_${R}.log 2>&1
+tail -1 gpurun_out/launches_${R}.log | cut -c1-200
+echo "=== full: gemm (the 4 shapes of the bench step at M=16384)"
+cat > /tmp/gemm_shapes.py <<'PY'
+import sys, torch
+sys.path.insert(0, '.')
+from mquant_b200 import ops
+M = 16384
+for K, N in ((4096, 4096), (4096, 11008), (11008, 4096)):
+    q = torch.randint(-128, 127, (M, K), dtype=torch.int8, device="cuda")
+    w4 = ops.pack_w4(torch.randint(-8, 7, (N, K), dtype=torch.int8, device="cuda"))
+    s_a = torch.rand(M, device="cuda") * 0.1
+    s_w = torch.rand(N, device="cuda") * 0.01
+    for _ in range(3):
+        ops.w4a8_gemm(q, w4, s_a, s_w, N)
+    torch.cuda.synchronize()
+PY
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:w4a8_gemm -f -o gpurun_out/prof_gemm_${R} python /tmp/gemm_shapes.py > gpurun_out/ncu_gemm_${R}.log 2>&1
 echo "=== full: hadamard tc + quant + minmax + fwht"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"hadk_tc_kernel|act_quant_i8_kernel|minmax_tensor_kernel|fwht_cta_kernel" -c 12 -f -o gpurun_out/prof_mem_${R} python tools/profile_target.py all 16384 > gpurun_out/ncu_mem_${R}.log 2>&1
 tail -2 gpurun_out/ncu_mem_${R}.log
-echo "=== gemm probes"
-for d in 0 1 16 4; do
-  echo "--- MQ_GEMM_DEBUG=$d" | tee -a gpurun_out/probe_${R}.log
-  MQ_GEMM_DEBUG=$d timeout 300 python tools/microbench.py --only gemm --quick 2>&1 | grep "M4096" | cut -c1-200 | tee -a gpurun_out/probe_${R}.log
-done
-ls -la gpurun_out | tail -12
+echo "=== microbench (all)"
+timeout 900 python tools/microbench.py --json gpurun_out/microbench_${R}.json > gpurun_out/microbench_${R}.log 2>&1
+tail -3 gpurun_out/microbench_${R}.log | cut -c1-200
+echo "=== bench"
+timeout 900 python bench.py > gpurun_out/bench_${R}.json 2> gpurun_out/bench_${R}.err
+cut -c1-300 gpurun_out/bench_${R}.json
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_${R}.json 2>/dev/null
+cut -c1-200 gpurun_out/bench_ref_${R}.json
+ls -la gpurun_out | tail -14
