@@ -39,7 +39,13 @@ constexpr int EPI_WARP0 = 8;
 constexpr int NUM_MID = 128;
 constexpr int NUM_EPI = 256;
 constexpr int TMEM_COLS = 512;
-constexpr int D2_COL0 = 0, D2_COL1 = 192, D1_COL = 384;  // D2 buffers (<= 176 cols), D1 region (128 cols)
+// TMEM plan (512 columns): two D2 accumulators (<= 176 columns each, at 0 and 192) + a 128-column
+// D1 ring.  (Tried: ONE D2 accumulator + a 256-column D1 ring so that all MMA1s of a unit issue
+// back to back -- 213 -> 257 us at M = 16384: MMA2 and the epilogue then serialise, and the
+// probes showed the bare barrier/TMA chain (103 us) is bound by bytes in flight, not by the D1
+// ping-pong.  profiles/r1_hadk_tc_probes.log)
+constexpr int D2B = 2;
+constexpr int D2_COL0 = 0, D1_COL = 384, D1_COLS = 128;
 
 struct Cfg {
   int had_k, Kpad, kb2;   // Kpad = round_up(had_k, 16); kb2 = ceil(Kpad / 64) k-blocks of hadK
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
   constexpr int S = P / 64;            // 64-wide j' segments per token
   constexpr int TPU = 2 / S;           // tokens per unit (one MMA2 tile = 2 segments)
-  constexpr int D1B = 128 / P;         // D1 ring depth (128 TMEM columns)
+  constexpr int D1B = D1_COLS / P;     // D1 ring depth
   constexpr int KB1 = P / 64;          // k-blocks of the MMA1 operands
   const HadArgs& a = prm.a;
   const Cfg& c = prm.c;
@@ -70,16 +76,16 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t sB1 = base + c.b1_off, sB2 = base + c.b2_off, sX = base + c.x_off, sT = base + c.t_off;
   const uint32_t bar0 = base + c.bar_off;
-  // barrier map: x_full[xs] x_empty[xs] d1_full[2] d1_empty[2] t_full[2] t_empty[2] d2_full[2] d2_empty[2]
+  // barrier map: x_full[xs] x_empty[xs] d1_full[4] d1_empty[4] t_full[2] t_empty[2] d2_full[2] d2_empty[2]
   auto x_full = [&](int s) { return bar0 + 8u * s; };
   auto x_empty = [&](int s) { return bar0 + 8u * (c.xs + s); };
   auto d1_full = [&](int s) { return bar0 + 8u * (2 * c.xs + s); };
-  auto d1_empty = [&](int s) { return bar0 + 8u * (2 * c.xs + 2 + s); };
-  auto t_full = [&](int s) { return bar0 + 8u * (2 * c.xs + 4 + s); };
-  auto t_empty = [&](int s) { return bar0 + 8u * (2 * c.xs + 6 + s); };
-  auto d2_full = [&](int s) { return bar0 + 8u * (2 * c.xs + 8 + s); };
-  auto d2_empty = [&](int s) { return bar0 + 8u * (2 * c.xs + 10 + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + c.bar_off + 8 * (2 * c.xs + 12));
+  auto d1_empty = [&](int s) { return bar0 + 8u * (2 * c.xs + 4 + s); };
+  auto t_full = [&](int s) { return bar0 + 8u * (2 * c.xs + 8 + s); };
+  auto t_empty = [&](int s) { return bar0 + 8u * (2 * c.xs + 10 + s); };
+  auto d2_full = [&](int s) { return bar0 + 8u * (2 * c.xs + 12 + s); };
+  auto d2_empty = [&](int s) { return bar0 + 8u * (2 * c.xs + 14 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + c.bar_off + 8 * (2 * c.xs + 16));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rtu = c.rt * TPU;  // row tiles per unit
@@ -92,9 +98,11 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       mbar_init(x_full(s), 1);
       mbar_init(x_empty(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(d1_full(s), 1);
       mbar_init(d1_empty(s), NUM_MID / 32);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(t_full(s), (NUM_MID / 32) * rtu);
       mbar_init(t_empty(s), 1);
       mbar_init(d2_full(s), 1);
@@ -195,15 +203,15 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
     const int pre = rtu < D1B ? rtu : D1B;  // row tiles of the NEXT unit issued ahead of MMA2
     if (my_units > 0) issue_mma1(rtu);
     for (int lu = 0; lu < my_units; ++lu) {
-      const int tb = lu % c.tb, d2 = lu & 1;
-      const uint32_t tph = (uint32_t)(lu / c.tb) & 1u, d2ph = (uint32_t)(lu >> 1) & 1u;
+      const int tb = lu % c.tb, d2 = lu % D2B;
+      const uint32_t tph = (uint32_t)(lu / c.tb) & 1u, d2ph = (uint32_t)(lu / D2B) & 1u;
       const bool more = lu + 1 < my_units;
       if (more) issue_mma1(pre);
       mbar_wait(t_full(tb), tph);
       mbar_wait(d2_empty(d2), d2ph ^ 1u);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t tm = tmem_base + (d2 ? D2_COL1 : D2_COL0);
+        const uint32_t tm = tmem_base + D2_COL0 + d2 * 192;
         const uint32_t tbase = sT + tb * c.t_buf;
         const uint32_t lbo = (prm.dbg & 1u) ? 1024u : (uint32_t)c.Kpad * 128u;
         const uint32_t sbo = (prm.dbg & 1u) ? (uint32_t)c.Kpad * 128u : 1024u;
@@ -236,8 +244,8 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
     const bool split = (a.flags & MQ_FLAG_SPLIT) != 0;
     int lu = 0;
     for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++lu) {
-      const int d2 = lu & 1;
-      const uint32_t d2ph = (uint32_t)(lu >> 1) & 1u;
+      const int d2 = lu % D2B;
+      const uint32_t d2ph = (uint32_t)(lu / D2B) & 1u;
       const int64_t tok = (S == 1) ? (u * TPU + seg) : u;
       const int j = (S == 1) ? jl : (seg * 64 + jl);
       const bool live = tok < a.M;
@@ -251,7 +259,7 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       if (live && j == 0 && grp == 0 && a.srow_out != nullptr) a.srow_out[tok] = qs.s;
       mbar_wait(d2_full(d2), d2ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(d2 ? D2_COL1 : D2_COL0);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D2_COL0 + d2 * 192);
       int8_t* obase = a.q + tok * (int64_t)a.n + (j - la);  // word-aligned: 4 consecutive j' per store
       auto process = [&](const uint32_t (&v)[16], int ch) {
         if (prm.dbg & 2u) return;  // probe: TMEM loads only
@@ -391,7 +399,7 @@ static int launch(const HadArgs& a, cudaStream_t st) {
   c.x_off = c.b2_off + b2;
   c.t_off = c.x_off + c.xs * c.x_stage;
   c.bar_off = c.t_off + c.tb * c.t_buf;
-  c.total = c.bar_off + 8 * (2 * c.xs + 12) + 16;
+  c.total = c.bar_off + 8 * (2 * c.xs + 16) + 16;
   const char* dbg_env = getenv("MQ_HAD_DEBUG");
   prm.dbg = dbg_env ? (unsigned)atoi(dbg_env) : 0u;
 
