@@ -39,6 +39,8 @@ SIGNATURES = {
     "mq_repack_w4_from_ref": (_i, [_p, _p, _i64, _i64, _p]),
     "mq_unpack_w4": (_i, [_p, _p, _i64, _i64, _i64, _p]),
     "mq_w4a8_gemm": (_i, [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
+    "mq_w4a8_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "mq_w4a8_gemm_ws": (_i, [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _sz, _p]),
     "mq_w4a8_gemm_simt": (_i, [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
 }
 

@@ -57,4 +57,9 @@ int launch_w4a8_gemm_v2(const CUtensorMap& tmap_a, const Params& p, cudaStream_t
 int launch_w4a8_gemm_v3(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st);
 
 }  // namespace gemm
+
+// mq_gemv_w4a8.cu: weight-streaming kernel for M <= 16 (split-K, int32 atomics in a workspace)
+size_t gemv_workspace_bytes(int64_t N);
+int launch_w4a8_gemv(const int8_t* qa, int64_t lda, const gemm::Params& g, void* workspace, cudaStream_t st);
+
 }  // namespace mq

@@ -291,9 +291,22 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
 }  // namespace gemm
 }  // namespace mq
 
+extern "C" size_t mq_w4a8_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  (void)K;
+  if (M <= 0 || M > 16 || N <= 0) return 0;
+  return mq::gemv_workspace_bytes(N);
+}
+
 extern "C" int mq_w4a8_gemm(const int8_t* qa, int64_t lda, const uint8_t* w4, const float* s_a, int s_a_per_row,
                             const float* s_w, const void* bias, const void* x0, const void* w0, void* out,
                             int64_t ldo, int64_t M, int64_t N, int64_t K, void* stream) {
+  return mq_w4a8_gemm_ws(qa, lda, w4, s_a, s_a_per_row, s_w, bias, x0, w0, out, ldo, M, N, K, nullptr, 0, stream);
+}
+
+extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4, const float* s_a, int s_a_per_row,
+                               const float* s_w, const void* bias, const void* x0, const void* w0, void* out,
+                               int64_t ldo, int64_t M, int64_t N, int64_t K, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   using namespace mq;
   using namespace mq::gemm;
   MQ_REQUIRE(qa && w4 && s_a && s_w && out, "mq_w4a8_gemm: null pointer");
@@ -335,10 +348,20 @@ extern "C" int mq_w4a8_gemm(const int8_t* qa, int64_t lda, const uint8_t* w4, co
   p.k_tiles = (int)(K / BK);
   const char* dbg_env = getenv("MQ_GEMM_DEBUG");
   p.dbg = dbg_env ? (unsigned)atoi(dbg_env) : 0u;
+  const char* kenv = getenv("MQ_GEMM_KERNEL");
+  // decode-sized batches: weight streaming with split-K when the caller provides the workspace
+  // (any MQ_GEMM_KERNEL override selects a tensor-core kernel instead).  Above 8 rows the dp4a rate
+  // starts to bind and the tcgen05 kernel wins once N gives it >= 32 CTAs (profiles/README.md).
+  const bool gemv_shape = M <= 8 || (M <= 16 && p.n_tiles < 32);
+  if (gemv_shape && workspace != nullptr && workspace_bytes >= gemv_workspace_bytes(N) && p.dbg == 0 && kenv == nullptr) {
+    const int rc = launch_w4a8_gemv(qa, lda, p, workspace, (cudaStream_t)stream);
+    if (rc != MQ_OK) return rc;
+    MQ_LAUNCH_CHECK("w4a8_gemv_kernel");
+    return MQ_OK;
+  }
   // Kernel selection (MQ_GEMM_KERNEL = v1 | v2 | 2cta overrides): v2 = 8-warp pipelined epilogue
   // with staged stores; 2cta = its cta_group::2 flavour (correct, but its TMA path currently
   // under-performs, profiles/README.md); v1 = this file's first-generation kernel.
-  const char* kenv = getenv("MQ_GEMM_KERNEL");
   int kernel = 2;  // default
   if (kenv) {
     if (kenv[0] == '2') kernel = 3;                         // "2cta"

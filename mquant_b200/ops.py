@@ -205,8 +205,31 @@ def w4a8_gemm(q, w4, s_a, s_w, N, bias=None, x0=None, w0=None, out=None, simt=Fa
     per_row = int(s_a.numel() == M)
     if out is None:
         out = torch.empty((M, N), dtype=torch.float16, device=q.device)
-    fn = lib().mq_w4a8_gemm_simt if simt else lib().mq_w4a8_gemm
-    check(fn(_ptr(q), q.stride(0) if M > 1 else max(K, q.stride(0)), _ptr(w4), _ptr(s_a), per_row, _ptr(s_w),
-             _ptr(bias), _ptr(x0), _ptr(w0), _ptr(out), out.stride(0) if M > 1 else max(N, out.stride(0)),
-             M, N, K, _stream()), "mq_w4a8_gemm")
+    lda = q.stride(0) if M > 1 else max(K, q.stride(0))
+    ldo = out.stride(0) if M > 1 else max(N, out.stride(0))
+    if simt:
+        check(lib().mq_w4a8_gemm_simt(_ptr(q), lda, _ptr(w4), _ptr(s_a), per_row, _ptr(s_w), _ptr(bias), _ptr(x0),
+                                      _ptr(w0), _ptr(out), ldo, M, N, K, _stream()), "mq_w4a8_gemm_simt")
+        return out
+    ws = _gemm_workspace(q.device, M, N, K)
+    check(lib().mq_w4a8_gemm_ws(_ptr(q), lda, _ptr(w4), _ptr(s_a), per_row, _ptr(s_w), _ptr(bias), _ptr(x0),
+                                _ptr(w0), _ptr(out), ldo, M, N, K, _ptr(ws), 0 if ws is None else ws.numel(),
+                                _stream()), "mq_w4a8_gemm")
     return out
+
+
+_gemm_ws = {}
+
+
+def _gemm_workspace(device, M, N, K):
+    """Zero-initialised, self-cleaning split-K workspace for decode-sized GEMMs (one per device and
+    stream, grown on demand)."""
+    need = lib().mq_w4a8_gemm_workspace_bytes(M, N, K)
+    if need == 0:
+        return None
+    key = (str(device), torch.cuda.current_stream().cuda_stream)
+    ws = _gemm_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        _gemm_ws[key] = ws
+    return ws

@@ -432,6 +432,22 @@ def test_gemm_tcgen05_matches_oracle(ops, monkeypatch, kernel, M, N, K, per_row,
     assert np.array_equal(bits16(got), bits16(oracle_gemm(case)))
 
 
+@pytest.mark.parametrize("M,N,K,per_row,bias,split", [
+    (1, 4096, 4096, False, True, False),
+    (3, 1000, 1152, True, False, True),      # ragged N, split rank-1 term
+    (16, 11008, 4096, True, True, False),
+    (9, 4096, 11008, True, False, False),
+])
+def test_gemm_decode_weight_streaming_path(ops, M, N, K, per_row, bias, split):
+    """M <= 16 takes the split-K dp4a kernel (int32 atomics in a self-cleaning workspace): bit-exact,
+    also when the same workspace is reused by back-to-back calls."""
+    rng = np.random.default_rng(M + N + K)
+    for rep in range(3):
+        case = gemm_case(rng, M, N, K, per_row, bias, split)
+        got = run_gemm(ops, case, simt=False)
+        assert np.array_equal(bits16(got), bits16(oracle_gemm(case))), rep
+
+
 def test_gemm_extreme_codes(ops):
     """Saturated operands: every activation -128, every weight -8 / +7 (largest |acc|)."""
     M, N, K = 128, 256, 19968

@@ -141,6 +141,29 @@ def main():
                 rec("w4a8_gemm", f"M{M} K{K} N{N}", sec, best, bytes_=N * K // 2 + M * K + 2 * M * N + 4 * N,
                     ops_=2 * M * N * K)
                 del q, codes, w4, out
+    if want("decode"):
+        import os
+        for K, N in [(4096, 4096), (4096, 11008), (11008, 4096)]:
+            codes = torch.randint(-8, 7, (N, K), dtype=torch.int8, device="cuda")
+            w4 = ops.pack_w4(codes)
+            s_w = torch.rand(N, device="cuda") * 0.01
+            for M in (1, 2, 4, 8, 16):
+                q = torch.randint(-128, 127, (M, K), dtype=torch.int8, device="cuda")
+                s_a = torch.rand(M, device="cuda") * 0.1
+                out = torch.empty(M, N, dtype=torch.float16, device="cuda")
+                for name, env in (("w4a8_gemv", None), ("w4a8_gemm_tc", "v2")):
+                    if env:
+                        os.environ["MQ_GEMM_KERNEL"] = env
+                    else:
+                        os.environ.pop("MQ_GEMM_KERNEL", None)
+                    sec, best = timeit(lambda: ops.w4a8_gemm(q, w4, s_a, s_w, N, out=out), flush=True, iters=20)
+                    rec(name, f"M{M} K{K} N{N}", sec, best, bytes_=N * K // 2 + M * K + 2 * M * N + 4 * N,
+                        ops_=2 * M * N * K)
+                os.environ.pop("MQ_GEMM_KERNEL", None)
+        # event-timing floor: an empty-ish launch after the L2 flush
+        z = torch.zeros(32, device="cuda")
+        sec, best = timeit(lambda: z.add_(1.0), flush=True, iters=20)
+        rec("timing_floor_tiny_kernel", "32 floats", sec, best, bytes_=256)
     if a.json:
         json.dump(rows, open(a.json, "w"), indent=1)
 
