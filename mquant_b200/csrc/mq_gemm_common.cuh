@@ -53,6 +53,9 @@ __device__ __forceinline__ void unpack_store(uint32_t brow, int rsw, int j, cons
 // mq_gemm_w4a8_v2.cu: second-generation kernel; two_cta selects the cta_group::2 flavour
 // (256 x 256 tile per CTA pair)
 int launch_w4a8_gemm_v2(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st, bool two_cta);
+// mq_gemm_w4a8_v4.cu: 256 x 256 tile per CTA, one converted weight k-block shared by two M halves
+// (tmap_out: fp16 output, 32 x 32 boxes, SWIZZLE_64B -- the epilogue stores through TMA)
+int launch_w4a8_gemm_v4(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out, const Params& p, cudaStream_t st);
 // mq_gemm_w4a8_v3.cu: register-path weights (no staging ring), two alternating converter groups
 int launch_w4a8_gemm_v3(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st);
 

@@ -359,15 +359,38 @@ extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4,
     MQ_LAUNCH_CHECK("w4a8_gemv_kernel");
     return MQ_OK;
   }
-  // Kernel selection (MQ_GEMM_KERNEL = v1 | v2 | 2cta overrides): v2 = 8-warp pipelined epilogue
-  // with staged stores; 2cta = its cta_group::2 flavour (correct, but its TMA path currently
+  // Kernel selection (MQ_GEMM_KERNEL = v1 | v2 | v3 | v4 | 2cta overrides): v4 = 256 x 256 tile, one
+  // weight conversion shared by two M halves (default for large M); v2 = 128 x 256 tile, 8-warp
+  // pipelined epilogue with staged stores (default below); 2cta = its cta_group::2 flavour (correct, but its TMA path currently
   // under-performs, profiles/README.md); v1 = this file's first-generation kernel.
-  int kernel = 2;  // default
+  // default: the 256 x 256 kernel once its tiles fill the machine 1.5 times (measured cross-over,
+  // profiles/README.md), else the 128 x 256 kernel
+  const int64_t tiles256 = ((M + 255) / 256) * (int64_t)p.n_tiles;
+  int kernel = 2 * tiles256 >= 3 * (int64_t)num_sms() ? 5 : 2;
   if (kenv) {
     if (kenv[0] == '2') kernel = 3;                         // "2cta"
     else if (kenv[0] == 'v' && kenv[1] == '1') kernel = 1;  // "v1"
     else if (kenv[0] == 'v' && kenv[1] == '3') kernel = 4;  // "v3"
+    else if (kenv[0] == 'v' && kenv[1] == '4') kernel = 5;  // "v4"
     else kernel = 2;                                        // "v2"
+  }
+  if (kernel == 5) {
+    // the 256 x 256 kernel writes its output with TMA: 32 x 32 fp16 boxes out of swizzled staging
+    CUtensorMap tmap_out;
+    const cuuint64_t odim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint64_t ostride[1] = {(cuuint64_t)ldo * 2};
+    const cuuint32_t obox[2] = {32, 32};
+    const CUresult cro = encode(&tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out, odim, ostride, obox, estride,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cro != CUDA_SUCCESS) {
+      set_error("mq_w4a8_gemm: cuTensorMapEncodeTiled (output) failed with CUresult %d", (int)cro);
+      return MQ_ERR_CUDA;
+    }
+    const int rc = launch_w4a8_gemm_v4(tmap, tmap_out, p, (cudaStream_t)stream);
+    if (rc != MQ_OK) return rc;
+    MQ_LAUNCH_CHECK("w4a8_gemm_v4_kernel");
+    return MQ_OK;
   }
   if (kernel == 4) {
     const int rc = launch_w4a8_gemm_v3(tmap, p, (cudaStream_t)stream);

@@ -411,7 +411,7 @@ def test_gemm_simt_matches_oracle(ops, M, N, K, per_row, bias, split):
     assert np.array_equal(bits16(O.qlinear_int(qa, s_a, cw, s_w, b, x0, w0)), bits16(oracle_gemm(case)))
 
 
-@pytest.mark.parametrize("kernel", ["default", "v1", "v2", "v3", "2cta"])
+@pytest.mark.parametrize("kernel", ["default", "v1", "v2", "v3", "v4", "2cta"])
 @pytest.mark.parametrize("M,N,K,per_row,bias,split", [
     (128, 256, 128, False, False, False),     # one tile, one k-block
     (128, 256, 512, False, False, False),     # pipeline wraps once
@@ -419,6 +419,7 @@ def test_gemm_simt_matches_oracle(ops, M, N, K, per_row, bias, split):
     (1, 256, 4096, False, True, False),       # decode-shaped
     (1000, 1000, 1152, True, False, True),    # ragged N (N % 256 != 0), split rank-1 term
     (2048, 4096, 4096, True, True, False),    # several tiles per CTA (both TMEM buffers, phases)
+    (600, 768, 640, True, True, True),        # 256-row tiles: last tile's second half is all padding
 ])
 def test_gemm_tcgen05_matches_oracle(ops, monkeypatch, kernel, M, N, K, per_row, bias, split):
     """Every tcgen05 kernel generation (the default and the opt-in ones kept for comparison) is

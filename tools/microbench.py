@@ -137,12 +137,12 @@ def main():
                 s_a = torch.rand(M, device="cuda") * 0.1
                 s_w = torch.rand(N, device="cuda") * 0.01
                 out = torch.empty(M, N, dtype=torch.float16, device="cuda")
+                kname = os.environ.get("MQ_GEMM_KERNEL", "default")
                 sec, best = timeit(lambda: ops.w4a8_gemm(q, w4, s_a, s_w, N, out=out), flush=True)
-                rec("w4a8_gemm", f"M{M} K{K} N{N}", sec, best, bytes_=N * K // 2 + M * K + 2 * M * N + 4 * N,
-                    ops_=2 * M * N * K)
+                rec(f"w4a8_gemm[{kname}]", f"M{M} K{K} N{N}", sec, best,
+                    bytes_=N * K // 2 + M * K + 2 * M * N + 4 * N, ops_=2 * M * N * K)
                 del q, codes, w4, out
     if want("decode"):
-        import os
         for K, N in [(4096, 4096), (4096, 11008), (11008, 4096)]:
             codes = torch.randint(-8, 7, (N, K), dtype=torch.int8, device="cuda")
             w4 = ops.pack_w4(codes)
