@@ -12,7 +12,7 @@ norms and activations are outside the path and are not run
 value      tokens/s of the whole job, inputs resident in HBM, CUDA-event timed, max over ranks
 e2e        same through the public API with HOST buffers: per step the token batch's hidden states
            are copied from pinned host memory and the last-token outputs are read back
-roofline   dominant kernel (w4a8_gemm_kernel): ops of all GEMM launches of a step / their summed
+roofline   dominant kernel (w4a8_gemm_v4_kernel): ops of all GEMM launches of a step / their summed
            CUDA-event durations, against 2 x the measured bf16 tensor peak (INT8 runs at twice the
            bf16 rate on B200; MEASURED_PEAKS.json has no INT8 entry)
 cpu_baseline  the oracle port of the reference's fake-quant layer on the host cores, bounded sample
@@ -262,18 +262,24 @@ def main():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         pk = json.load(open(peaks_path))
-        peak = 2.0 * float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)))
-        peak_src = "2 x measured bf16_tflops_sustained (MEASURED_PEAKS.json; INT8 = 2x bf16 rate, no INT8 entry)"
+        # No INT8 entry in MEASURED_PEAKS.json: INT8 issues at twice the bf16 rate.  The in-step GEMM
+        # EXCEEDS 2 x the *sustained* bf16 figure (that run was power limited at 1290 MHz; the INT8
+        # kernel holds ~1800 MHz), so the valid upper bound is 2 x the burst figure; the
+        # sustained-derived fraction is reported next to it.
+        peak = 2.0 * float(pk.get("bf16_tflops", 1590.0))
+        peak_sus = 2.0 * float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)))
+        peak_src = "2 x measured bf16_tflops burst (MEASURED_PEAKS.json; INT8 = 2x bf16 rate, no INT8 entry)"
     else:
-        peak, peak_src = 2.0 * 1400.0, "2 x fallback sustained bf16 (B200_PROFILING.md)"
+        peak, peak_sus, peak_src = 2.0 * 1590.0, 2.0 * 1400.0, "2 x fallback bf16 (B200_PROFILING.md)"
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per
     # launch, averaged over the step's shape mix); only meaningful for the default workload
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1b_gemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1c_gemm_traffic.json")
     if os.path.exists(tpath) and a.tokens == 16384:
         traffic = json.load(open(tpath)).get("avg_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "w4a8_gemm_v2_kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "tensor", "kernel": "w4a8_gemm_v4_kernel", "achieved": achieved, "peak": peak,
                 "unit": "TOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "peak_2x_bf16_sustained": peak_sus, "frac_2x_bf16_sustained": achieved / peak_sus,
                 "peak_nominal": 4500.0, "frac_nominal": achieved / 4500.0,
                 "avg_launch_ms": gemm_total_ms / max(n_gemm, 1), "launches_timed": n_gemm,
                 "share_of_step": gemm_total_ms / ms_step}

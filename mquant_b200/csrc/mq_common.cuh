@@ -166,16 +166,26 @@ __device__ __forceinline__ uint4 pack8_f16(const float (&f)[8]) {
 // 8 halfs (one uint4) -> 8 int8 codes (one uint2); bit-exact w.r.t. quant_code_exact
 __device__ __forceinline__ uint2 quant8(const uint4& v, const QScale& q) {
   const __half2* h = reinterpret_cast<const __half2*>(&v);
-  uint32_t t[8], d[8];
+  uint32_t t[8];
   uint32_t diff = 0;
+  // both ends of the bracket for two elements per instruction (sm_100 packed fp32 FMA: each half
+  // is an ordinary round-to-nearest fma)
+  uint64_t inv_lo2, inv_hi2, magic2;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(inv_lo2) : "f"(q.inv_lo));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(inv_hi2) : "f"(q.inv_hi));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(magic2) : "f"(MQ_RND_MAGIC));
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float2 f = __half22float2(__hmin2(__hmax2(h[i], q.lim_lo), q.lim_hi));
-    t[2 * i] = __float_as_uint(__fmaf_rn(f.x, q.inv_lo, MQ_RND_MAGIC));
-    t[2 * i + 1] = __float_as_uint(__fmaf_rn(f.y, q.inv_lo, MQ_RND_MAGIC));
-    d[2 * i] = t[2 * i] ^ __float_as_uint(__fmaf_rn(f.x, q.inv_hi, MQ_RND_MAGIC));
-    d[2 * i + 1] = t[2 * i + 1] ^ __float_as_uint(__fmaf_rn(f.y, q.inv_hi, MQ_RND_MAGIC));
-    diff |= d[2 * i] | d[2 * i + 1];
+    uint64_t x, lo, hi;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(f.x), "f"(f.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(lo) : "l"(x), "l"(inv_lo2), "l"(magic2));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(hi) : "l"(x), "l"(inv_hi2), "l"(magic2));
+    uint32_t h0, h1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(t[2 * i]), "=r"(t[2 * i + 1]) : "l"(lo));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(h0), "=r"(h1) : "l"(hi));
+    diff |= t[2 * i] ^ h0;  // (a ^ b) | diff is one LOP3
+    diff |= t[2 * i + 1] ^ h1;
   }
   // Undecided elements (the bracket straddles a half-integer: mostly quotients that round to an
   // exact tie, ~1e-4 .. 1e-2 of elements depending on how "round" the scale is) take the true
@@ -183,10 +193,9 @@ __device__ __forceinline__ uint2 quant8(const uint4& v, const QScale& q) {
   if (diff != 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      if (d[i] != 0) {
-        const float x = __half2float(reinterpret_cast<const __half*>(&v)[i]);
-        t[i] = q8_exact(x, q.s);
-      }
+      const float x = __half2float(reinterpret_cast<const __half*>(&v)[i]);
+      const float xc = fminf(fmaxf(x, __low2float(q.lim_lo)), __low2float(q.lim_hi));
+      if (t[i] != __float_as_uint(__fmaf_rn(xc, q.inv_hi, MQ_RND_MAGIC))) t[i] = q8_exact(x, q.s);
     }
   }
   uint2 r;

@@ -375,8 +375,10 @@ extern "C" int mq_hadamard_quant_i8(const void* x, int64_t ldx, int8_t* q, void*
         set_error("mq_hadamard_quant_i8: power-of-two n=%d outside [64, 8192]", n);
         return MQ_ERR_UNSUPPORTED;
     }
-  } else if (hadk_tc_supported(a)) {
-    rc = launch_hadk_tc(a, st);  // both Kronecker factors on tcgen05
+  } else if (const char* hk = getenv("MQ_HAD_KERNEL"); hk && hk[0] == 't' && hk[2] == '1' && hadk_tc_supported(a)) {
+    rc = launch_hadk_tc(a, st);  // "tc1": both Kronecker factors on tcgen05 (kept for comparison)
+  } else if (hadk_tc2_supported(a) && (rc = launch_hadk_tc2(a, st)) != MQ_ERR_UNSUPPORTED) {
+    // FWHT of the power-of-two factor in registers + hadK on tcgen05
   } else {
     switch (logp) {
       case 3: case 4: case 5:

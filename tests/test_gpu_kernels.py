@@ -253,9 +253,16 @@ def test_hadamard_pow2(ops, n):
     had_check(ops, x, n, 1, s, fp32_had=True)
 
 
+@pytest.mark.parametrize("path", ["default", "simt"])
 @pytest.mark.parametrize("n,n_in", [(11008, 11008), (13824, 13696), (14336, 14336), (19968, 18944),
-                                    (5120, 5120), (3584, 3584)])
-def test_hadamard_nonpow2(ops, n, n_in):
+                                    (5120, 5120), (3584, 3584), (3072, 3072), (5120 * 2, 5120 * 2)])
+def test_hadamard_nonpow2(ops, monkeypatch, path, n, n_in):
+    """default = FWHT in registers + hadK on tcgen05 (mq_hadamard_tc2.cu; P = 64 .. 512),
+    simt = the CUDA-core kernel."""
+    if path == "simt":
+        monkeypatch.setenv("MQ_HAD_SIMT", "1")
+    else:
+        monkeypatch.delenv("MQ_HAD_SIMT", raising=False)
     k = O.get_hadK(n)[1]
     assert k > 1
     rng = np.random.default_rng(n)
@@ -271,9 +278,11 @@ def test_hadamard_nonpow2(ops, n, n_in):
 
 @pytest.mark.parametrize("n,n_in,M", [(11008, 11008, 9), (11008, 11008, 300), (13824, 13696, 5),
                                       (19968, 18944, 7), (5120, 5120, 33), (3584, 3584, 130)])
-def test_hadamard_nonpow2_tensor_core_path(ops, n, n_in, M):
-    """codes-only requests with n/had_k in {64,128} run both Kronecker factors on tcgen05
-    (mq_hadamard_tc.cu); compare with the CUDA-core kernel and with the oracle."""
+@pytest.mark.parametrize("kernel", ["tc2", "tc1"])
+def test_hadamard_nonpow2_tensor_core_path(ops, monkeypatch, kernel, n, n_in, M):
+    """codes-only requests on the tensor-core kernels (tc2 = default: FWHT in registers + hadK on
+    tcgen05; tc1 = both Kronecker factors on tcgen05, n/had_k in {64,128}); compare with the
+    CUDA-core kernel and with the oracle."""
     from mquant_b200 import hadamard_utils as hu
 
     k = O.get_hadK(n)[1]
@@ -286,10 +295,16 @@ def test_hadamard_nonpow2_tensor_core_path(ops, n, n_in, M):
     scales = ops.make_scales(float(s), float(s_vis), "cuda")
     xd, md = dev(x), dev(mod)
     for split in (False, True):
+        monkeypatch.delenv("MQ_HAD_SIMT", raising=False)
+        if kernel == "tc1":
+            monkeypatch.setenv("MQ_HAD_KERNEL", "tc1")
         tc = ops.hadamard(xd, had_k=k, hadk=hk, n=n, scales=scales, modality=md, want_codes=True,
                           want_f16=False, split=split)
+        monkeypatch.delenv("MQ_HAD_KERNEL", raising=False)
+        monkeypatch.setenv("MQ_HAD_SIMT", "1")
         ref = ops.hadamard(xd, had_k=k, hadk=hk, n=n, scales=scales, modality=md, want_codes=True,
-                           want_f16=True, split=split)  # fp16 output requested -> CUDA-core kernel
+                           want_f16=True, split=split)  # CUDA-core kernel
+        monkeypatch.delenv("MQ_HAD_SIMT", raising=False)
         q_tc, q_ref = host(tc["q"]).astype(np.int32), host(ref["q"]).astype(np.int32)
         d = np.abs(q_tc - q_ref)
         assert d.max() <= 1, d.max()
