@@ -4,7 +4,7 @@ R=${1:-r1}
 mkdir -p gpurun_out
 echo "=== launch list (bench, 2 layers): our kernels only, warm-up skipped"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none \
-  -k regex:"w4a8_gemm|act_quant_i8_kernel|hadk_tc_kernel" -s 84 -c 28 --csv \
+  -k regex:"w4a8_gemm|act_quant_i8_kernel|hadk_tc" -s 84 -c 28 --csv \
   --log-file gpurun_out/launches_${R}.csv python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_${R}.log 2>&1
 tail -1 gpurun_out/launches_${R}.log | cut -c1-200
 echo "=== full: gemm (the 4 shapes of the bench step at M=16384)"
@@ -24,7 +24,7 @@ for K, N in ((4096, 4096), (4096, 11008), (11008, 4096)):
 PY
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:w4a8_gemm -f -o gpurun_out/prof_gemm_${R} python /tmp/gemm_shapes.py > gpurun_out/ncu_gemm_${R}.log 2>&1
 echo "=== full: hadamard tc + quant + minmax + fwht"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"hadk_tc_kernel|act_quant_i8_kernel|minmax_tensor_kernel|fwht_cta_kernel" -c 12 -f -o gpurun_out/prof_mem_${R} python tools/profile_target.py all 16384 > gpurun_out/ncu_mem_${R}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"hadk_tc2_kernel|act_quant_i8_kernel|minmax_tensor_kernel|fwht_cta_kernel" -c 12 -f -o gpurun_out/prof_mem_${R} python tools/profile_target.py all 16384 > gpurun_out/ncu_mem_${R}.log 2>&1
 tail -2 gpurun_out/ncu_mem_${R}.log
 echo "=== microbench (all)"
 timeout 900 python tools/microbench.py --json gpurun_out/microbench_${R}.json > gpurun_out/microbench_${R}.log 2>&1
