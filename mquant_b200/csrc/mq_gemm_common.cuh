@@ -56,6 +56,11 @@ int launch_w4a8_gemm_v2(const CUtensorMap& tmap_a, const Params& p, cudaStream_t
 // mq_gemm_w4a8_v4.cu: 256 x 256 tile per CTA, one converted weight k-block shared by two M halves
 // (tmap_out: fp16 output, 32 x 32 boxes, SWIZZLE_64B -- the epilogue stores through TMA)
 int launch_w4a8_gemm_v4(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out, const Params& p, cudaStream_t st);
+// mq_gemm_w4a8_sk.cu: split-K flavour of the 128 x 256 kernel for mid-sized M (int32 partial sums in
+// a caller-provided self-cleaning workspace); splitk_factor() == 1 means "not worth it"
+int splitk_factor(int64_t M, int64_t N, int64_t K);
+size_t splitk_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int launch_w4a8_gemm_sk(const CUtensorMap& tmap_a, const Params& p, void* workspace, cudaStream_t st);
 // mq_gemm_w4a8_v3.cu: register-path weights (no staging ring), two alternating converter groups
 int launch_w4a8_gemm_v3(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st);
 

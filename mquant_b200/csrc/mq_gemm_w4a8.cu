@@ -292,9 +292,11 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
 }  // namespace mq
 
 extern "C" size_t mq_w4a8_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-  (void)K;
-  if (M <= 0 || M > 16 || N <= 0) return 0;
-  return mq::gemv_workspace_bytes(N);
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  // one call uses at most one of the two (both leave the workspace zeroed), so they may alias
+  const size_t a = M <= 16 ? mq::gemv_workspace_bytes(N) : 0;
+  const size_t b = K % mq::gemm::BK == 0 ? mq::gemm::splitk_workspace_bytes(M, N, K) : 0;
+  return a > b ? a : b;
 }
 
 extern "C" int mq_w4a8_gemm(const int8_t* qa, int64_t lda, const uint8_t* w4, const float* s_a, int s_a_per_row,
@@ -357,6 +359,14 @@ extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4,
     const int rc = launch_w4a8_gemv(qa, lda, p, workspace, (cudaStream_t)stream);
     if (rc != MQ_OK) return rc;
     MQ_LAUNCH_CHECK("w4a8_gemv_kernel");
+    return MQ_OK;
+  }
+  // mid-sized M: too few tiles for the persistent kernels -> split K across CTAs
+  if (kenv == nullptr && p.dbg == 0 && workspace != nullptr && splitk_factor(M, N, K) >= 2 &&
+      workspace_bytes >= splitk_workspace_bytes(M, N, K)) {
+    const int rc = launch_w4a8_gemm_sk(tmap, p, workspace, (cudaStream_t)stream);
+    if (rc != MQ_OK) return rc;
+    MQ_LAUNCH_CHECK("w4a8_gemm_sk_kernel");
     return MQ_OK;
   }
   // Kernel selection (MQ_GEMM_KERNEL = v1 | v2 | v3 | v4 | 2cta overrides): v4 = 256 x 256 tile, one

@@ -464,6 +464,26 @@ def test_gemm_decode_weight_streaming_path(ops, M, N, K, per_row, bias, split):
         assert np.array_equal(bits16(got), bits16(oracle_gemm(case))), rep
 
 
+@pytest.mark.parametrize("M,N,K,per_row,bias,split", [
+    (64, 4096, 4096, True, False, False),
+    (200, 1000, 2304, True, True, True),     # ragged M and N, split rank-1 term, uneven K slices
+    (256, 4096, 11008, False, True, False),  # uneven K slices (86 k-blocks)
+    (500, 768, 2048, True, False, True),
+    (17, 4096, 11008, True, True, False),
+])
+def test_gemm_split_k_path(ops, M, N, K, per_row, bias, split):
+    """Mid-sized M takes the split-K kernel (int32 partial sums in the self-cleaning workspace,
+    the last CTA of a tile applies the epilogue): bit-exact, also back to back on one workspace."""
+    from mquant_b200._lib import lib
+
+    assert lib().mq_w4a8_gemm_workspace_bytes(M, N, K) > 0
+    rng = np.random.default_rng(M + N + K)
+    for rep in range(3):
+        case = gemm_case(rng, M, N, K, per_row, bias, split)
+        got = run_gemm(ops, case, simt=False)
+        assert np.array_equal(bits16(got), bits16(oracle_gemm(case))), rep
+
+
 def test_gemm_extreme_codes(ops):
     """Saturated operands: every activation -128, every weight -8 / +7 (largest |acc|)."""
     M, N, K = 128, 256, 19968
