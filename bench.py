@@ -44,7 +44,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tokens", type=int, default=16384, help="tokens per GPU per step (16 x 1024)")
     ap.add_argument("--seq-len", type=int, default=1024)
-    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--layers", type=int, default=None, help="default: the model's layer count")
+    ap.add_argument("--workload", default="qwenvl-9.6b", choices=["qwenvl-9.6b", "qwen2vl-7b", "internvl2-8b"],
+                    help="qwenvl-9.6b = BASELINE configs[1] (the bench line); the others are the LLM shapes "
+                         "of configs[3]/[2], with --dynamic-visual for Qwen2-VL's dynamic-resolution spans")
+    ap.add_argument("--dynamic-visual", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -92,6 +96,7 @@ def run_reference_arm(a):
         return
     cores = os.cpu_count() or 1
     tokens = 1024
+    a.layers = a.layers or 32
     for _ in range(min(a.warmup, 1)):
         cpu_layer_sample(tokens)
     ts = [cpu_layer_sample(tokens) for _ in range(max(1, min(a.steps, 3)))]
@@ -184,8 +189,10 @@ def main():
     from mquant_b200.prefill import QuantLinearStack
 
     dev = torch.device("cuda", local_rank)
-    stack = QuantLinearStack("qwenvl-9.6b", n_layers=a.layers, device=dev)
-    inputs = stack.make_inputs(a.tokens, dev, seed=100 + rank, seq_len=a.seq_len)
+    stack = QuantLinearStack(a.workload, n_layers=a.layers, device=dev)
+    a.layers = stack.n_layers
+    inputs = stack.make_inputs(a.tokens, dev, seed=100 + rank, seq_len=a.seq_len,
+                               visual_span="dynamic" if a.dynamic_visual else 256)
     n_seq = max(1, a.tokens // a.seq_len)
 
     def barrier():
@@ -288,8 +295,9 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8xint4->int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "tokens_per_gpu_per_step": a.tokens, "seq_len": a.seq_len,
-                   "visual_tokens_per_seq": 256, "layers": a.layers, "parallelism": f"dp{world}",
+        "config": {"workload": WORKLOAD if a.workload == "qwenvl-9.6b" else stack.describe(),
+                   "tokens_per_gpu_per_step": a.tokens, "seq_len": a.seq_len,
+                   "visual_tokens_per_seq": "dynamic 64..seq_len/2" if a.dynamic_visual else 256, "layers": a.layers, "parallelism": f"dp{world}",
                    "l2": "inputs+weights per step (>3 GB) exceed the 126 MB L2; no flush needed"},
         "ttft_ms_per_request": ms_step / n_seq,
         "clocks": clocks,
@@ -299,7 +307,7 @@ def main():
         "gpu_launches": stack.launches_per_step() * a.steps,
         "roofline": roofline,
     }
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and a.workload == "qwenvl-9.6b":
         cores = os.cpu_count() or 1
         tok = 1024
         per_layer = cpu_layer_sample(tok)

@@ -109,6 +109,16 @@ int mq_hadamard_quant_i8(const void* x, int64_t ldx, int8_t* q, void* y_f16, flo
 int mq_observer_minmax(const void* x, int64_t ldx, int64_t M, int C, int per_channel,
                        float* minmax_io, void* stream);
 
+/* The same for Modality-Specific Static scales (layer_wise only): ONE pass merges the rows with
+ * modality[m] == 0 into minmax_text_io and the others into minmax_visual_io (each float[2]
+ * {min, max}) and adds the number of rows of either kind to seen_io (unsigned[2] {text, visual}),
+ * so that the host needs neither x[mask] gathers nor a device round trip to learn whether a
+ * modality occurred.  Replaces two MinmaxObserver.update calls (minmax.py:13-28) on the two
+ * halves of the batch. */
+int mq_observer_minmax_msq(const void* x, int64_t ldx, int64_t M, int C, const uint8_t* modality,
+                           float* minmax_text_io, float* minmax_visual_io, unsigned* seen_io,
+                           void* stream);
+
 /* PercentileObserver.update's order statistics (percentile.py:31-32): exact
  * torch.quantile(v.flatten().float(), q) for q in {alpha, 1-alpha}, linear interpolation,
  * via a two-pass counting select on the fp16 bit patterns.  out = float[2] {q_lo, q_hi}

@@ -89,6 +89,81 @@ minmax_tensor_kernel(const __half* __restrict__ x, int64_t ldx, int64_t M, int C
   }
 }
 
+// layer_wise with Modality-Specific Static scales: one pass over x updates the text pair and the
+// visual pair (row m belongs to modality[m]) and counts the rows of either kind -- the host never
+// has to gather x[mask] / x[~mask] or to ask the device whether a modality occurred.
+// Thread = (row, 8-element chunk); rows are walked by warps so that the modality byte is a
+// warp-uniform broadcast load.
+__global__ void __launch_bounds__(256)
+minmax_tensor_msq_kernel(const __half* __restrict__ x, int64_t ldx, int64_t M, int C,
+                         const uint8_t* __restrict__ modality, float* __restrict__ io_text,
+                         float* __restrict__ io_vis, unsigned* __restrict__ seen) {
+  const int chunks_per_row = C >> 3;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t warp_id = (int64_t)blockIdx.x * 8 + w, n_warps = (int64_t)gridDim.x * 8;
+  __half2 mx[2] = {__float2half2_rn(0.f), __float2half2_rn(0.f)};
+  __half2 mn[2] = {__float2half2_rn(0.f), __float2half2_rn(0.f)};
+  unsigned rows[2] = {0u, 0u};
+  for (int64_t m = warp_id; m < M; m += n_warps) {
+    const int kind = modality[m] != 0 ? 1 : 0;
+    rows[kind] += (lane == 0);
+    const __half* xr = x + m * ldx;
+    __half2 rmx = __float2half2_rn(0.f), rmn = rmx;
+    // 4 independent 128-bit loads in flight per thread
+    for (int c0 = lane; c0 < chunks_per_row; c0 += 128) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + 32 * u;
+        v[u] = c < chunks_per_row ? ldg_stream(xr + ((int64_t)c << 3)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          rmx = __hmax2(rmx, h[i]);
+          rmn = __hmin2(rmn, h[i]);
+        }
+      }
+    }
+    mx[kind] = __hmax2(mx[kind], rmx);
+    mn[kind] = __hmin2(mn[kind], rmn);
+  }
+  __shared__ float smx[2][8], smn[2][8];
+  __shared__ unsigned srows[2][8];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    float fmx = fmaxf(__low2float(mx[k]), __high2float(mx[k]));
+    float fmn = fminf(__low2float(mn[k]), __high2float(mn[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      fmx = fmaxf(fmx, __shfl_xor_sync(0xffffffffu, fmx, o));
+      fmn = fminf(fmn, __shfl_xor_sync(0xffffffffu, fmn, o));
+    }
+    if (lane == 0) {
+      smx[k][w] = fmx;
+      smn[k][w] = fmn;
+      srows[k][w] = rows[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int k = threadIdx.x;
+    float fmx = 0.f, fmn = 0.f;
+    unsigned r = 0;
+    for (int i = 0; i < 8; ++i) {
+      fmx = fmaxf(fmx, smx[k][i]);
+      fmn = fminf(fmn, smn[k][i]);
+      r += srows[k][i];
+    }
+    float* io = k ? io_vis : io_text;
+    merge_min(io + 0, fmn);
+    merge_max(io + 1, fmx);
+    if (r) atomicAdd(seen + k, r);
+  }
+}
+
 // channel_wise: io = {min[C], max[C]}.  blockIdx.x -> 2048-channel slab (256 threads x 8
 // channels), blockIdx.y -> row slice; each thread keeps its 8 channels in registers.
 __global__ void __launch_bounds__(256)
@@ -281,6 +356,24 @@ extern "C" int mq_observer_minmax(const void* x, int64_t ldx, int64_t M, int C, 
     minmax_channel_kernel<<<grid, 256, 0, st>>>((const __half*)x, ldx, M, C, minmax_io);
   }
   MQ_LAUNCH_CHECK("minmax kernel");
+  return MQ_OK;
+}
+
+extern "C" int mq_observer_minmax_msq(const void* x, int64_t ldx, int64_t M, int C, const uint8_t* modality,
+                                      float* minmax_text_io, float* minmax_visual_io, unsigned* seen_io,
+                                      void* stream) {
+  using namespace mq;
+  MQ_REQUIRE(x && modality && minmax_text_io && minmax_visual_io && seen_io, "mq_observer_minmax_msq: null pointer");
+  MQ_REQUIRE(M >= 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldx >= C,
+             "mq_observer_minmax_msq: need C%%8==0 and ldx%%8==0 (C=%d ldx=%lld)", C, (long long)ldx);
+  MQ_REQUIRE(aligned16(x), "mq_observer_minmax_msq: x must be 16-byte aligned");
+  if (M == 0) return MQ_OK;
+  int64_t blocks = (M + 7) / 8;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  minmax_tensor_msq_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, ldx, M, C, modality, minmax_text_io, minmax_visual_io, seen_io);
+  MQ_LAUNCH_CHECK("minmax_tensor_msq_kernel");
   return MQ_OK;
 }
 

@@ -74,6 +74,13 @@ def merge_calibration(model, group=None, channels_hint=None):
     obs = _minmax_observers(model)
     if not obs:
         return 0
+    # which modality each MSQ quantizer has seen, as known on the host (gather path), BEFORE
+    # missing observer states are zero-filled below
+    for _, layer in find_qlayers(model, layers=[ActQuantWrapper]).items():
+        q = layer.quantizer
+        if getattr(q, "static", False) and getattr(q, "msq", False) and getattr(q, "_seen", None) is None:
+            q._seen_host = (int(q.observer.max_val is not None),
+                            int(q.observer_visual is not None and q.observer_visual.max_val is not None))
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     dev = None
     for _, o in obs:
@@ -97,6 +104,16 @@ def merge_calibration(model, group=None, channels_hint=None):
     merge_observer_states([o.state for o in live], group)
     for o in live:
         o._refresh()
+    # row counts of the fused text/visual observer (which modality has been seen anywhere)
+    if distributed:
+        for _, layer in sorted(find_qlayers(model, layers=[ActQuantWrapper]).items()):
+            q = layer.quantizer
+            if getattr(q, "static", False) and getattr(q, "msq", False) and q.observer.state is not None:
+                if getattr(q, "_seen", None) is None:
+                    # a rank that used the gather path knows on the host what it saw
+                    q._seen = torch.tensor(list(getattr(q, "_seen_host", (0, 0))), dtype=torch.int32,
+                                           device=q.observer.state.device)
+                dist.all_reduce(q._seen, op=dist.ReduceOp.SUM, group=group)
     # the scales were last derived from rank-local statistics: recompute them from the merged ones
     for _, layer in find_qlayers(model, layers=[ActQuantWrapper]).items():
         q = layer.quantizer

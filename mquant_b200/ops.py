@@ -127,6 +127,18 @@ def observer_minmax(x, state, per_channel=False):
     return state
 
 
+def observer_minmax_msq(x, modality, state_text, state_visual, seen):
+    """mq_observer_minmax_msq: one pass, rows with modality == 0 -> state_text, others ->
+    state_visual (fp32 [2] each), row counts added to `seen` (int32 [2])."""
+    _need_cuda(x, modality, state_text, state_visual, seen)
+    assert x.dtype == torch.float16 and modality.dtype == torch.uint8 and seen.dtype == torch.int32
+    x2 = _as_rows(x)
+    M, C = x2.shape
+    assert modality.numel() == M and state_text.numel() == 2 and state_visual.numel() == 2 and seen.numel() == 2
+    check(lib().mq_observer_minmax_msq(_ptr(x2), _ld(x2), M, C, _ptr(modality), _ptr(state_text),
+                                       _ptr(state_visual), _ptr(seen), _stream()), "mq_observer_minmax_msq")
+
+
 _pct_ws = {}
 
 

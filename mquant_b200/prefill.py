@@ -21,22 +21,50 @@ import torch
 
 from . import hadamard_utils, msq, quant_utils
 
-SHAPES = {
-    # name: (hidden, ffn, n_layers, qkv_bias)   -- SURVEY.md appendix B
-    "qwenvl-9.6b": (4096, 11008, 32, True),
-}
-
-# (name, in, out, bias, online_hadamard, input buffer kind)
-def _linears(hidden, ffn, qkv_bias):
+# Linear inventories of the LLMs named by BASELINE.json configs 2-4.
+# Each entry: (name, in_features, out_features, bias, online_hadamard, input buffer kind); an
+# online-Hadamard input narrower than auto_pad_size(in) is zero padded (utils.revise_down_input,
+# folded into the fused kernel through QuantLinear.pad_to).
+def _qwenvl(hidden=4096, ffn=11008):
     return [
-        ("attn.q_proj", hidden, hidden, qkv_bias, False, "h"),
-        ("attn.k_proj", hidden, hidden, qkv_bias, False, "h"),
-        ("attn.v_proj", hidden, hidden, qkv_bias, False, "h"),
+        ("attn.q_proj", hidden, hidden, True, False, "h"),
+        ("attn.k_proj", hidden, hidden, True, False, "h"),
+        ("attn.v_proj", hidden, hidden, True, False, "h"),
         ("attn.c_proj", hidden, hidden, False, False, "a"),
         ("mlp.w1", hidden, ffn, False, False, "h2"),
         ("mlp.w2", hidden, ffn, False, False, "h2"),
-        ("mlp.c_proj", ffn, hidden, False, True, "f"),
+        ("mlp.c_proj", ffn, hidden, False, True, "f"),   # 11008 = 172 x 64
     ]
+
+
+def _qwen2vl(hidden=3584, ffn=18944, kv=512):
+    return [
+        ("self_attn.q_proj", hidden, hidden, True, False, "h"),
+        ("self_attn.k_proj", hidden, kv, True, False, "h"),
+        ("self_attn.v_proj", hidden, kv, True, False, "h"),
+        ("self_attn.o_proj", hidden, hidden, False, False, "a"),
+        ("mlp.gate_proj", hidden, ffn, False, False, "h2"),
+        ("mlp.up_proj", hidden, ffn, False, False, "h2"),
+        ("mlp.down_proj", ffn, hidden, False, True, "f"),  # 18944 -> padded 19968 = 156 x 128
+    ]
+
+
+def _internvl2(hidden=4096, ffn=14336, qkv=6144):
+    return [
+        ("attention.wqkv", hidden, qkv, False, False, "h"),
+        ("attention.wo", hidden, hidden, False, False, "a"),
+        ("feed_forward.w1", hidden, ffn, False, False, "h2"),
+        ("feed_forward.w3", hidden, ffn, False, False, "h2"),
+        ("feed_forward.w2", ffn, hidden, False, True, "f"),  # 14336 = 28 x 512
+    ]
+
+
+MODELS = {
+    # name: (hidden, ffn, n_layers, linears)
+    "qwenvl-9.6b": (4096, 11008, 32, _qwenvl()),
+    "qwen2vl-7b": (3584, 18944, 28, _qwen2vl()),
+    "internvl2-8b": (4096, 14336, 32, _internvl2()),
+}
 
 
 class _Args:
@@ -52,20 +80,30 @@ def synthetic_tokens(n_tokens, width, device, seed=0, visual_span=256, seq_len=1
     idx = torch.arange(7, width, 997, device=device)
     x[:, idx] *= 20
     mask = torch.zeros(n_tokens, dtype=torch.uint8, device=device)
-    for s in range(0, n_tokens, seq_len):
+    spans = None
+    if visual_span == "dynamic":
+        # Qwen2-VL dynamic resolution: (H/28)*(W/28) visual tokens per image, drawn per sequence
+        gs = torch.Generator().manual_seed(seed)
+        n_seq = (n_tokens + seq_len - 1) // seq_len
+        spans = torch.randint(64, max(65, seq_len // 2), (n_seq,), generator=gs).tolist()
+    for i, s in enumerate(range(0, n_tokens, seq_len)):
         a = s + 1
-        mask[a:min(a + visual_span, n_tokens, s + seq_len)] = 1
+        span = spans[i] if spans is not None else visual_span
+        mask[a:min(a + span, n_tokens, s + seq_len)] = 1
     return x.half(), mask
 
 
 class QuantLinearStack(torch.nn.Module):
     def __init__(self, model="qwenvl-9.6b", n_layers=None, device="cuda", seed=42, calib_tokens=2048,
-                 split=False, keep_fp16_weights=False):
+                 split=False, keep_fp16_weights=False, calibrate=True):
+        """calibrate=False leaves the wrappers configured (static INT8, MSQ, minmax observers) but
+        neither calibrated nor frozen -- the starting point of a (sharded) calibration run."""
         super().__init__()
-        hidden, ffn, L, qkv_bias = SHAPES[model]
+        hidden, ffn, L, spec = MODELS[model]
+        self.model = model
         self.hidden, self.ffn = hidden, ffn
         self.n_layers = L if n_layers is None else n_layers
-        self.spec = _linears(hidden, ffn, qkv_bias)
+        self.spec = spec
         self.layers = torch.nn.ModuleList()
         torch.manual_seed(seed)
         args = _Args()
@@ -79,13 +117,18 @@ class QuantLinearStack(torch.nn.Module):
         for _ in range(self.n_layers):
             block = torch.nn.ModuleDict()
             for name, k_in, n_out, bias, had, kind in self.spec:
-                lin = torch.nn.Linear(k_in, n_out, bias=bias).half().to(device)
+                k_pad = hadamard_utils.auto_pad_size(k_in) if had else k_in
+                lin = torch.nn.Linear(k_pad, n_out, bias=bias).half().to(device)
+                if k_pad != k_in:
+                    lin.weight.data[:, k_in:] = 0  # the padded input columns are zero anyway
                 w = quant_utils.ActQuantWrapper(lin)
                 if had:
                     # offline: rotate the weight so that the online transform cancels
                     hadamard_utils.apply_exact_had_to_linear(lin, had_dim=-1, output=False)
                     w.online_full_had = True
-                    w.had_K, w.K = hadamard_utils.get_hadK(k_in)
+                    w.had_K, w.K = hadamard_utils.get_hadK(k_pad)
+                    if k_pad != k_in:
+                        w.pad_to = k_pad
                     if split:
                         w.split = True
                         w.split_weights()
@@ -95,6 +138,10 @@ class QuantLinearStack(torch.nn.Module):
                 wq.find_params(tgt.weight.data)
                 tgt.weight.data = wq.quantize(tgt.weight.data).to(torch.float16)
                 w.quantizer.configure(bits=8, sym=True, static=True, observer_type="minmax", msq=True)
+                w._wq_scale = wq.scale
+                if not calibrate:
+                    block[name.replace(".", "_")] = w
+                    continue
                 with msq.modality_context(cmask):
                     quant_utils.calibrate_static(w, args, [calib[kind]], forward=lambda m, b: m(b))
                 w.freeze(wq.scale)
@@ -124,6 +171,24 @@ class QuantLinearStack(torch.nn.Module):
                 for name, _, _, _, _, kind in self.spec:
                     out = block[name.replace(".", "_")](inputs[kind])
         return out
+
+    @torch.no_grad()
+    def observe_tokens(self, inputs):
+        """Calibration pass of the hot path only: online rotation (fp16 output) + observer update of
+        every wrapper, without the fp16 Linear the reference's calibration forward also runs (that
+        GEMM is the caller's model compute, not the path).  Wrappers must be in calibrate mode."""
+        with msq.modality_context(inputs["mask"]):
+            for block in self.layers:
+                for name, _, _, _, _, kind in self.spec:
+                    w = block[name.replace(".", "_")]
+                    w.quantizer(w._rotate(inputs[kind]))
+
+    def describe(self):
+        had = [(n, k) for n, k, _, _, h, _ in self.spec if h][0]
+        kp = hadamard_utils.auto_pad_size(had[1])
+        return (f"{self.model} LLM prefill, quantized-linear path ({len(self.spec)} QuantLinear x {self.n_layers} layers, "
+                f"W4A8, MSQ, online Hadamard on {had[0]}: {had[1]}"
+                + (f" padded to {kp}" if kp != had[1] else "") + f", K={hadamard_utils.get_hadK(kp)[1]})")
 
     def gemm_ops_per_token(self):
         return sum(2 * k * n for _, k, n, _, _, _ in self.spec) * self.n_layers

@@ -150,15 +150,44 @@ class ActQuantizer(torch.nn.Module):
             self.observer.update(x)
             return
         x2 = x.reshape(-1, x.shape[-1])
+        if self._fused_msq_ok(x2):
+            # one kernel: both modalities' min/max and the row counts of either kind, no gathers
+            # and no device round trip (mq_observer_minmax_msq)
+            for o in (self.observer, self.observer_visual):
+                if o.state is None:
+                    o.state = torch.zeros(2, dtype=torch.float32, device=x.device)
+                    o._dtype, o._channels = x.dtype, x2.shape[-1]
+            if getattr(self, "_seen", None) is None:
+                self._seen = torch.zeros(2, dtype=torch.int32, device=x.device)
+            ops.observer_minmax_msq(x2, mod, self.observer.state, self.observer_visual.state, self._seen)
+            self.observer._refresh()
+            self.observer_visual._refresh()
+            return
         vis = mod.bool()
         if bool((~vis).any()):
             self.observer.update(x2[~vis])
         if bool(vis.any()):
             self.observer_visual.update(x2[vis])
 
-    def update_quantization_params(self):
+    def _fused_msq_ok(self, x2):
+        from .observer.minmax import MinmaxObserver
+        return (type(self.observer) is MinmaxObserver and type(self.observer_visual) is MinmaxObserver
+                and not self.observer._per_channel() and x2.is_cuda and x2.dtype == torch.float16
+                and x2.shape[-1] % 8 == 0 and x2.stride(-1) == 1)
+
+    def _seen_kinds(self):
+        """(text seen, visual seen).  The fused observer counts rows on the device: one read here,
+        when the parameters are derived, instead of one per observed batch."""
         has_t = self.observer.max_val is not None
         has_v = self.msq and self.observer_visual.max_val is not None
+        seen = getattr(self, "_seen", None)
+        if seen is not None:
+            n_t, n_v = seen.tolist()
+            has_t, has_v = has_t and n_t > 0, has_v and n_v > 0
+        return has_t, has_v
+
+    def update_quantization_params(self):
+        has_t, has_v = self._seen_kinds()
         if has_t:
             self.quantizer.update_quantization_params()
         if has_v:

@@ -343,6 +343,30 @@ def test_matmul_hadU_cuda_api(ops, golden):
     np.testing.assert_allclose(host(y), ref, atol=2e-5)
 
 
+def test_observer_minmax_msq_fused(ops):
+    """One pass for both modalities (mq_observer_minmax_msq) == two MinmaxObservers on x[~mask] and
+    x[mask]; row counts tell which modality occurred."""
+    rng = np.random.default_rng(11)
+    st_t = torch.zeros(2, device="cuda")
+    st_v = torch.zeros(2, device="cuda")
+    seen = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ot, ov = O.MinmaxObserver(), O.MinmaxObserver()
+    n_t = n_v = 0
+    for M, C, frac in [(300, 4096, 0.3), (17, 11008, 0.0), (1024, 512, 0.9), (5, 64, 1.0)]:
+        x = rnd_act(rng, M, C)
+        mod = (rng.random(M) < frac).astype(np.uint8)
+        ops.observer_minmax_msq(dev(x), dev(mod), st_t, st_v, seen)
+        if (mod == 0).any():
+            ot.update(x[mod == 0])
+        if (mod != 0).any():
+            ov.update(x[mod != 0])
+        n_t += int((mod == 0).sum())
+        n_v += int((mod != 0).sum())
+    assert host(seen).tolist() == [n_t, n_v]
+    assert np.array_equal(host(st_t), np.array([ot.min_val, ot.max_val], dtype=np.float32))
+    assert np.array_equal(host(st_v), np.array([ov.min_val, ov.max_val], dtype=np.float32))
+
+
 # ------------------------------------------------------------------------------- weights
 def test_weight_rtn_and_pack(ops, golden):
     g = golden("weight_quant")

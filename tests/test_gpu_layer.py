@@ -123,3 +123,43 @@ def test_qwenvl_mlp_down_proj_layer(qu):
         cos, err = cos_maxabs(y_real.cpu().numpy(), y_fake.cpu().numpy())
         assert cos >= 0.9999, (split, cos, err)
         assert err <= 2.0 ** -9 * float(y_fake.abs().max()) * 4, (split, err)
+
+
+@pytest.mark.parametrize("model,had_name,k_in,k_pad,had_k", [
+    ("qwen2vl-7b", "mlp_down_proj", 18944, 19968, 156),       # BASELINE config 4: padded down_proj
+    ("internvl2-8b", "feed_forward_w2", 14336, 14336, 28),    # BASELINE config 3: 28 x 512
+])
+@torch.no_grad()
+def test_other_llm_shapes_through_the_stack(qu, model, had_name, k_in, k_pad, had_k):
+    """One block of the Qwen2-VL / InternVL2 LLM built through the drop-in API: the online-Hadamard
+    Linear (padded input, dynamic-resolution modality mask) on the integer path against the
+    reference-equivalent fake-quant path of the same wrapper, and the GEMM bit-exact against the
+    integer oracle on the kernel's own codes."""
+    from mquant_b200 import hadamard_utils as hu, msq, ops
+    from mquant_b200.prefill import QuantLinearStack
+
+    stack = QuantLinearStack(model, n_layers=1, device="cuda", calib_tokens=512, keep_fp16_weights=True)
+    w = stack.layers[0][had_name]
+    assert w.K == had_k and (w.pad_to or k_in) == k_pad and w.real_quant
+    inputs = stack.make_inputs(384, "cuda", seed=5, visual_span="dynamic", seq_len=128)
+    x, mask = inputs["f"], inputs["mask"]
+    assert x.shape[1] == k_in and 0 < int(mask.sum()) < mask.numel()
+    with msq.modality_context(mask):
+        y_real = w(x.clone())
+        w.real_quant = False
+        y_fake = w(x.clone())
+        w.real_quant = True
+    cos, err = cos_maxabs(y_real.cpu().numpy(), y_fake.cpu().numpy())
+    assert cos >= 0.9999 and err <= 2.0 ** -9 * float(y_fake.abs().max()) * 4, (cos, err)
+    # integer oracle on the kernel's own codes and per-token scales
+    qz = w.quantizer.quantizer
+    hk = hu.hadK_device(w.K, "cuda")
+    r = ops.hadamard(x, had_k=w.K, hadk=hk, n=k_pad, scales=qz.device_scales(x.device), modality=mask,
+                     want_codes=True, want_f16=False, want_row_scales=True)
+    pk = w._packed
+    cw = ops.unpack_w4(pk["w4"], pk["N"], pk["Kp"]).cpu().numpy()
+    want = O.qlinear_int(r["q"].cpu().numpy(), r["s_row"].cpu().numpy(), cw[:, :k_pad], pk["s_w"].cpu().numpy().reshape(-1), None)
+    assert np.array_equal(y_real.cpu().numpy().view(np.uint16), want.view(np.uint16))
+    # the whole block runs
+    out = stack.forward_tokens(inputs)
+    assert out.shape == (384, stack.hidden) and torch.isfinite(out).all()
