@@ -163,3 +163,70 @@ def test_other_llm_shapes_through_the_stack(qu, model, had_name, k_in, k_pad, ha
     # the whole block runs
     out = stack.forward_tokens(inputs)
     assert out.shape == (384, stack.hidden) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("split", [False, True])
+@torch.no_grad()
+def test_packed_checkpoint_round_trip(qu, tmp_path, split):
+    """save_packed -> load_packed into a freshly wrapped model (different random weights, never
+    calibrated): bit-identical outputs on the integer path; the file holds INT4 codes in the
+    reference's pack_i4 order, scales and the static text/visual activation scales only."""
+    import mquant_b200
+    from mquant_b200 import hadamard_utils as hu, msq
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1 = torch.nn.Linear(256, 768, bias=True)
+            self.fc2 = torch.nn.Linear(768, 256, bias=False)
+
+        def forward(self, x):
+            return self.fc2(torch.nn.functional.silu(self.fc1(x)))
+
+    def build(seed):
+        torch.manual_seed(seed)
+        net = Net().half().cuda()
+        qu.add_actquant(net)
+        return net
+
+    args = type("A", (), {"skip_names": []})()
+    net = build(0)
+    w2 = net.fc2
+    hu.apply_exact_had_to_linear(w2.module, had_dim=-1, output=False)
+    w2.online_full_had = True
+    w2.had_K, w2.K = hu.get_hadK(768)
+    assert w2.K == 12
+    if split:
+        w2.split = True
+        w2.split_weights()
+    wqs = {}
+    for name, w in (("fc1", net.fc1), ("fc2", w2)):
+        tgt = w.L2 if (w.split) else w.module
+        wq = qu.WeightQuantizer()
+        wq.configure(4, perchannel=True, sym=True, mse=False)
+        wq.find_params(tgt.weight.data)
+        tgt.weight.data = wq.quantize(tgt.weight.data).to(torch.float16)
+        w.quantizer.configure(bits=8, sym=True, static=True, observer_type="minmax", msq=True)
+        wqs[name] = wq
+    x = (torch.randn(2, 96, 256, device="cuda") * 2).half()
+    mask = torch.zeros(192, dtype=torch.uint8, device="cuda")
+    mask[10:70] = 1
+    with msq.modality_context(mask):
+        qu.calibrate_static(net, args, [x, x * 0.7])
+        net.fc1.freeze(wqs["fc1"].scale)
+        w2.freeze(wqs["fc2"].scale)
+        y0 = net(x.clone())
+    path = str(tmp_path / "packed.pt")
+    assert mquant_b200.save_packed(net, path) == 2
+    sd = torch.load(path, weights_only=True)
+    assert sd["fc2.w4"].dtype == torch.uint8 and tuple(sd["fc2.w4"].shape) == (256, 768 // 2)
+    assert sd["fc1.act_scale"].numel() == 2 and not any(v.dtype == torch.float16 and v.numel() > 4096 for v in sd.values())
+    # codes in the file are the reference's interchange format
+    cw = qu.unpack_i4(sd["fc1.w4"])[:, :256].to(torch.float32)
+    assert torch.equal((cw * sd["fc1.s_w"][:, None]).half(), net.fc1.module.weight.data.cpu())
+    fresh = build(123)
+    assert mquant_b200.load_packed(fresh, path) == 2
+    assert fresh.fc2.real_quant and fresh.fc2.K == 12 and fresh.fc2.split == split
+    with msq.modality_context(mask):
+        y1 = fresh(x.clone())
+    assert torch.equal(y0.view(torch.int16), y1.view(torch.int16))
