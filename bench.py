@@ -49,6 +49,9 @@ def parse():
                     help="qwenvl-9.6b = BASELINE configs[1] (the bench line); the others are the LLM shapes "
                          "of configs[3]/[2], with --dynamic-visual for Qwen2-VL's dynamic-resolution spans")
     ap.add_argument("--dynamic-visual", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true",
+                    help="do not share the activation quantisation / GEMM launch between the Linears of a "
+                         "block that read the same tensor (q/k/v, the two up projections)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -189,7 +192,7 @@ def main():
     from mquant_b200.prefill import QuantLinearStack
 
     dev = torch.device("cuda", local_rank)
-    stack = QuantLinearStack(a.workload, n_layers=a.layers, device=dev)
+    stack = QuantLinearStack(a.workload, n_layers=a.layers, device=dev, fuse_siblings=not a.no_fuse)
     a.layers = stack.n_layers
     inputs = stack.make_inputs(a.tokens, dev, seed=100 + rank, seq_len=a.seq_len,
                                visual_span="dynamic" if a.dynamic_visual else 256)
@@ -298,6 +301,7 @@ def main():
         "config": {"workload": WORKLOAD if a.workload == "qwenvl-9.6b" else stack.describe(),
                    "tokens_per_gpu_per_step": a.tokens, "seq_len": a.seq_len,
                    "visual_tokens_per_seq": "dynamic 64..seq_len/2" if a.dynamic_visual else 256, "layers": a.layers, "parallelism": f"dp{world}",
+                   "sibling_fusion": not a.no_fuse,
                    "l2": "inputs+weights per step (>3 GB) exceed the 126 MB L2; no flush needed"},
         "ttft_ms_per_request": ms_step / n_seq,
         "clocks": clocks,

@@ -95,9 +95,11 @@ def synthetic_tokens(n_tokens, width, device, seed=0, visual_span=256, seq_len=1
 
 class QuantLinearStack(torch.nn.Module):
     def __init__(self, model="qwenvl-9.6b", n_layers=None, device="cuda", seed=42, calib_tokens=2048,
-                 split=False, keep_fp16_weights=False, calibrate=True):
+                 split=False, keep_fp16_weights=False, calibrate=True, fuse_siblings=False):
         """calibrate=False leaves the wrappers configured (static INT8, MSQ, minmax observers) but
-        neither calibrated nor frozen -- the starting point of a (sharded) calibration run."""
+        neither calibrated nor frozen -- the starting point of a (sharded) calibration run.
+        fuse_siblings=True lets the Linears of a block that read the same tensor (q/k/v, the two
+        up projections) share one activation quantisation and one GEMM launch (bit-identical)."""
         super().__init__()
         hidden, ffn, L, spec = MODELS[model]
         self.model = model
@@ -150,6 +152,13 @@ class QuantLinearStack(torch.nn.Module):
                     for lin_ in ([w.module] + ([w.L1, w.L2] if w.split else [])):
                         lin_.weight.data = torch.empty(0, dtype=torch.float16, device=device)
                 block[name.replace(".", "_")] = w
+            if fuse_siblings and calibrate:
+                by_input = {}
+                for name, _, _, _, had, kind in self.spec:
+                    if not had:
+                        by_input.setdefault(kind, []).append(block[name.replace(".", "_")])
+                for group in by_input.values():
+                    quant_utils.fuse_siblings(group)
             self.layers.append(block)
 
     def make_inputs(self, n_tokens, device="cuda", seed=0, visual_span=256, seq_len=1024):
@@ -194,5 +203,16 @@ class QuantLinearStack(torch.nn.Module):
         return sum(2 * k * n for _, k, n, _, _, _ in self.spec) * self.n_layers
 
     def launches_per_step(self):
-        # per Linear: one activation kernel (quant or fused Hadamard+quant) + one GEMM
-        return 2 * len(self.spec) * self.n_layers
+        # per Linear (or per fused sibling group): one activation kernel (quant or fused
+        # Hadamard+quant) + one GEMM
+        units = 0
+        seen = set()
+        for name, *_ in self.spec:
+            w = self.layers[0][name.replace(".", "_")]
+            g = getattr(w, "_group", None)
+            if g is None:
+                units += 1
+            elif id(g) not in seen:
+                seen.add(id(g))
+                units += 1
+        return 2 * units * self.n_layers

@@ -262,6 +262,7 @@ class ActQuantWrapper(torch.nn.Module):
         self.pad_to = None       # fold utils.revise_down_input into the fused kernel
         self.real_quant = False  # set by freeze()
         self._packed = None
+        self._group = None       # set by fuse_siblings()
 
     def extra_repr(self) -> str:
         s = f"Input Quantizer Bits: {self.quantizer.bits}"
@@ -330,6 +331,8 @@ class ActQuantWrapper(torch.nn.Module):
         return self
 
     def _forward_real(self, x):
+        if self._group is not None:
+            return self._group.forward(self, x)
         pk = self._packed
         qz = self.quantizer.quantizer
         x2 = x.reshape(-1, x.shape[-1])
@@ -632,6 +635,99 @@ def model_quant(model, args):
 
 def model_no_quant(model, args):
     return _set_flag(model, args, "quant", False)
+
+
+class _SiblingGroup:
+    """Frozen QuantLinears that are always fed the SAME tensor (q/k/v, gate/up): the first member
+    called with an input quantises it once and runs ONE W4A8 GEMM over the concatenated output
+    channels; the siblings called next with that very tensor get their column slice of the result
+    (one int8 write shared by 3 resp. 2 GEMMs).  Results are bit-identical to
+    separate calls: same codes, same scales, same per-channel epilogue.
+
+    "The same tensor" is decided by object identity + version counter; the group keeps a reference
+    to the input while results are pending, so the address cannot be recycled meanwhile."""
+
+    def __init__(self, members):
+        self.members = list(members)
+        first = members[0]
+        pks = [m._packed for m in members]
+        self.offsets, off = [], 0
+        for pk in pks:
+            self.offsets.append(off)
+            off += pk["N"]
+        self.N = off
+        self.Kp = pks[0]["Kp"]
+        self.w4 = torch.cat([pk["w4"] for pk in pks])  # tile-major layout: n-blocks are contiguous
+        self.s_w = torch.cat([pk["s_w"].reshape(-1) for pk in pks]).contiguous()
+        if any(pk["bias"] is not None for pk in pks):
+            self.bias = torch.cat([pk["bias"] if pk["bias"] is not None else
+                                   torch.zeros(pk["N"], dtype=torch.float16, device=self.w4.device) for pk in pks])
+            # adding an exact +0.0 bias leaves every fp32 sum unchanged (no -0.0 can occur: the
+            # accumulator term is +-finite or +0.0)
+        else:
+            self.bias = None
+        self.first = first
+        self._x = None
+        self._ver = None
+        self._out = None
+        self._served = set()
+
+    def release(self):
+        self._x = self._out = self._ver = None
+        self._served = set()
+
+    @torch.no_grad()
+    def forward(self, member, x):
+        idx = self.members.index(member)
+        hit = (self._x is x and self._ver == x._version and idx not in self._served)
+        if not hit:
+            w = self.first
+            qz = w.quantizer.quantizer
+            x2 = x.reshape(-1, x.shape[-1])
+            scales = qz.device_scales(x.device)
+            modality = w.quantizer._modality(x) if qz.scale_visual is not None else None
+            q, srow, _ = ops.act_quant_i8(x2, scales, modality, n_out=self.Kp, split=False,
+                                          want_row_scales=modality is not None)
+            s_a = srow if modality is not None else scales[0:1]
+            self._out = ops.w4a8_gemm(q, self.w4, s_a, self.s_w, self.N, bias=self.bias)
+            self._x, self._ver, self._served = x, x._version, set()
+        self._served.add(idx)
+        N = member._packed["N"]
+        y = self._out[:, self.offsets[idx]:self.offsets[idx] + N].reshape(*x.shape[:-1], N)
+        if len(self._served) == len(self.members):
+            self.release()
+        return y
+
+
+def fuse_siblings(wrappers):
+    """Make frozen wrappers that read the same input share one activation quantisation and one
+    GEMM launch (see _SiblingGroup).  Refuses (returns None, leaves the wrappers untouched) unless
+    it is exact: identical static scales, no online rotation / split, same K, output widths that
+    are multiples of the 256-channel weight tile (the last one may be ragged)."""
+    wrappers = list(wrappers)
+    if len(wrappers) < 2:
+        return None
+    f = wrappers[0]
+    for i, w in enumerate(wrappers):
+        if not (isinstance(w, ActQuantWrapper) and w.real_quant and w._group is None):
+            return None
+        if w.online_full_had or w.online_partial_had or w.split or w.out_quantizer.bits < 16:
+            return None
+        if w._packed["Kp"] != f._packed["Kp"] or w._packed["K"] != f._packed["K"]:
+            return None
+        if i < len(wrappers) - 1 and w._packed["N"] % 256 != 0:
+            return None
+        a, b = w.quantizer.quantizer, f.quantizer.quantizer
+        if w.quantizer.msq != f.quantizer.msq or not torch.equal(a.scale.float().cpu(), b.scale.float().cpu()):
+            return None
+        if (a.scale_visual is None) != (b.scale_visual is None):
+            return None
+        if a.scale_visual is not None and not torch.equal(a.scale_visual.float().cpu(), b.scale_visual.float().cpu()):
+            return None
+    g = _SiblingGroup(wrappers)
+    for w in wrappers:
+        w._group = g
+    return g
 
 
 @torch.no_grad()

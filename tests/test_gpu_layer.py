@@ -230,3 +230,34 @@ def test_packed_checkpoint_round_trip(qu, tmp_path, split):
     with msq.modality_context(mask):
         y1 = fresh(x.clone())
     assert torch.equal(y0.view(torch.int16), y1.view(torch.int16))
+
+
+@torch.no_grad()
+def test_sibling_fusion_is_bit_identical(qu):
+    """q/k/v and the two up projections of a block share one activation quantisation and one GEMM
+    launch when fused; outputs must not change by a bit, also when the input is
+    modified in place between calls or a sibling is skipped."""
+    from mquant_b200.prefill import QuantLinearStack
+
+    plain = QuantLinearStack("qwenvl-9.6b", n_layers=1, device="cuda", calib_tokens=256)
+    fused = QuantLinearStack("qwenvl-9.6b", n_layers=1, device="cuda", calib_tokens=256, fuse_siblings=True)
+    assert fused.launches_per_step() == 8 and plain.launches_per_step() == 14
+    inputs = plain.make_inputs(300, "cuda", seed=3, seq_len=100, visual_span=40)
+    from mquant_b200 import msq
+    with msq.modality_context(inputs["mask"]):
+        for name, _, _, _, _, kind in plain.spec:
+            key = name.replace(".", "_")
+            a = plain.layers[0][key](inputs[kind])
+            b = fused.layers[0][key](inputs[kind])
+            assert b.shape == a.shape and torch.equal(a.view(torch.int16), b.contiguous().view(torch.int16)), name
+        # in-place change of the shared input between sibling calls: no stale result
+        blk_p, blk_f = plain.layers[0], fused.layers[0]
+        h = inputs["h"].clone()
+        q1 = blk_f["attn_q_proj"](h)
+        h.mul_(0.5)
+        k1 = blk_f["attn_k_proj"](h)
+        assert torch.equal(k1.contiguous().view(torch.int16), blk_p["attn_k_proj"](h).view(torch.int16))
+        # a different tensor object with equal content is a different input
+        v1 = blk_f["attn_v_proj"](h.clone())
+        assert torch.equal(v1.contiguous().view(torch.int16), blk_p["attn_v_proj"](h).view(torch.int16))
+        assert q1.shape == (300, 4096)
