@@ -84,7 +84,7 @@ w4a8_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) {
   const uint32_t sW = base + SM_W;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEMPTR);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler: role code stays on the uniform datapath
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
 

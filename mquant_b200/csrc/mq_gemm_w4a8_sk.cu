@@ -63,7 +63,8 @@ w4a8_gemm_sk_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p, 
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEMPTR);
   volatile uint32_t* last_flag = reinterpret_cast<volatile uint32_t*>(smem + SM_FLAG);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const int total_work = p.m_tiles * p.n_tiles * sp.ksplit;
   // work item w -> tile t = w / ksplit (mb = t / n_tiles, nb = t % n_tiles), k-blocks [kb0, kb1)
   auto k_range = [&](int w, int& t, int& kb0, int& kb1) {

@@ -127,7 +127,7 @@ w4a8_gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) 
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 * WSTAGES + 2 + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::SM_TMEMPTR);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler: role code stays on the uniform datapath
   const int lane = threadIdx.x & 31;
   const uint32_t cta = TWO ? cluster_ctarank() : 0u;  // 0 = leader
   const int unit = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // CTA or CTA pair

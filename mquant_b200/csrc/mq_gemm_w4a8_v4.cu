@@ -83,7 +83,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   auto tempty_bar = [&](int h) { return bar0 + 8u * (2 * ASTAGES + 2 * BSTAGES + 2 * WSTAGES + 2 + h); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEMPTR);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler: role code stays on the uniform datapath
   const int lane = threadIdx.x & 31;
   const int unit = (int)blockIdx.x;
   const int num_units = (int)gridDim.x;

@@ -87,7 +87,8 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
   auto d2_empty = [&](int s) { return bar0 + 8u * (2 * c.xs + 14 + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + c.bar_off + 8 * (2 * c.xs + 16));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const int rtu = c.rt * TPU;  // row tiles per unit
   const int64_t n_units = (a.M + TPU - 1) / TPU;
 

@@ -117,7 +117,8 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
   auto d2_empty = [&](int s) { return bar0 + 8u * (2 * XSTAGES + 6 + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + c.bar_off + 8 * (2 * XSTAGES + 8));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const int64_t n_units = (a.M + TPU - 1) / TPU;
   const int my_units = blockIdx.x < n_units ? (int)((n_units - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 

@@ -459,6 +459,7 @@ def test_gemm_simt_matches_oracle(ops, M, N, K, per_row, bias, split):
     (1000, 1000, 1152, True, False, True),    # ragged N (N % 256 != 0), split rank-1 term
     (2048, 4096, 4096, True, True, False),    # several tiles per CTA (both TMEM buffers, phases)
     (600, 768, 640, True, True, True),        # 256-row tiles: last tile's second half is all padding
+    (5000, 1024, 2048, True, False, False),   # many tiles per CTA, ragged M
 ])
 def test_gemm_tcgen05_matches_oracle(ops, monkeypatch, kernel, M, N, K, per_row, bias, split):
     """Every tcgen05 kernel generation (the default and the opt-in ones kept for comparison) is
