@@ -4,7 +4,7 @@ R=${1:-r1}
 mkdir -p gpurun_out
 echo "=== launch list (bench, 2 layers): our kernels only, warm-up skipped"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none \
-  -k regex:"w4a8_gemm|act_quant_i8_kernel|hadk_tc" -s 84 -c 28 --csv \
+  -k regex:"w4a8_gemm|act_quant_i8_kernel|hadk_tc" -s 48 -c 16 --csv \
   --log-file gpurun_out/launches_${R}.csv python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_${R}.log 2>&1
 tail -1 gpurun_out/launches_${R}.log | cut -c1-200
 echo "=== full: gemm (the 4 shapes of the bench step at M=16384)"
@@ -13,7 +13,7 @@ import sys, torch
 sys.path.insert(0, '.')
 from mquant_b200 import ops
 M = 16384
-for K, N in ((4096, 4096), (4096, 11008), (11008, 4096)):
+for K, N in ((4096, 12288), (4096, 4096), (4096, 22016), (11008, 4096)):  # q|k|v, o, w1|w2 (sibling fused), down
     q = torch.randint(-128, 127, (M, K), dtype=torch.int8, device="cuda")
     w4 = ops.pack_w4(torch.randint(-8, 7, (N, K), dtype=torch.int8, device="cuda"))
     s_a = torch.rand(M, device="cuda") * 0.1
