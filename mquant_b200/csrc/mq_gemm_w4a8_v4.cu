@@ -329,6 +329,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * BN + col0);
         uint32_t va[32], vb[32];
         tmem_ld32_nowait(taddr, va);
+        const uint64_t sa2p = f2_pack(sa, sa), x0v2p = f2_pack(x0v, x0v);
         auto process = [&](const uint32_t (&v)[32], int cc) {
           const int colb = col0 + cc * 32;
           if (p.dbg & 32u) return;  // probe: TMEM drain only
@@ -341,14 +342,27 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = colb + g * 8;
+            // the two multiplications handle two columns per instruction (packed fp32: each half
+            // rounds like the scalar op); the additions stay scalar -- ptxas contracts
+            // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the .rn qualifiers, which changes 1 in
+            // 10^4 outputs by an fp16 ulp (test_gemm_tcgen05_matches_oracle caught it)
             float y[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float sc = __fmul_rn(sa, ps[col + e]);
-              float val = __fmul_rn((float)(int)v[g * 8 + e], sc);
-              if (has_r1) val = __fadd_rn(val, __fmul_rn(x0v, __half2float(ps_w0[col + e])));
-              if (has_bias) val = __fadd_rn(val, __half2float(ps_bias[col + e]));
-              y[e] = val;
+            for (int e = 0; e < 8; e += 2) {
+              const uint64_t sc = f2_mul(sa2p, f2_pack(ps[col + e], ps[col + e + 1]));
+              f2_unpack(f2_mul(f2_pack((float)(int)v[g * 8 + e], (float)(int)v[g * 8 + e + 1]), sc), y[e], y[e + 1]);
+              if (has_r1) {
+                const float2 w0f = __half22float2(*reinterpret_cast<const __half2*>(ps_w0 + col + e));
+                float t0, t1;
+                f2_unpack(f2_mul(x0v2p, f2_pack(w0f.x, w0f.y)), t0, t1);
+                y[e] = __fadd_rn(y[e], t0);
+                y[e + 1] = __fadd_rn(y[e + 1], t1);
+              }
+              if (has_bias) {
+                const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(ps_bias + col + e));
+                y[e] = __fadd_rn(y[e], bf.x);
+                y[e + 1] = __fadd_rn(y[e + 1], bf.y);
+              }
             }
             const uint4 hv = pack8_f16(y);
             const uint32_t dst = stg + lane * 64 + ((uint32_t)(g ^ ((lane >> 1) & 3)) << 4);
