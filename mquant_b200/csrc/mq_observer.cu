@@ -247,22 +247,48 @@ __device__ __forceinline__ void wanted_ranks(int64_t n, double alpha, int64_t (&
   w[1] = rk_hi - floorf(rk_hi);
 }
 
-__global__ void pct_select_kernel(unsigned* __restrict__ ws, int64_t n, double alpha) {
-  // single thread: 4096-bin scan (negligible)
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// One block of 1024 threads, 4 coarse bins each: block-wide exclusive scan of the counts, then every
+// thread looks for the four wanted ranks inside its own bins.  (The first version walked the 4096
+// bins with one thread -- 4096 dependent global loads, 0.3 ms of the 0.37 ms a small call took.)
+__global__ void __launch_bounds__(1024) pct_select_kernel(unsigned* __restrict__ ws, int64_t n, double alpha) {
+  static_assert(kCoarseBins == 4096, "4 bins per thread of a 1024-thread block");
+  __shared__ unsigned long long warp_tot[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint4 c4 = reinterpret_cast<const uint4*>(ws)[t];
+  const unsigned c[4] = {c4.x, c4.y, c4.z, c4.w};
+  unsigned long long s = (unsigned long long)c[0] + c[1] + c[2] + c[3];
+  unsigned long long inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    unsigned long long v = warp_tot[lane], iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, iv, o);
+      if (lane >= o) iv += u;
+    }
+    warp_tot[lane] = iv - v;  // exclusive prefix of the warp totals
+  }
+  __syncthreads();
+  int64_t cum = (int64_t)(warp_tot[w] + inc - s);  // elements in the bins before this thread's
   int64_t r[4];
-  float w[2];
-  wanted_ranks(n, alpha, r, w);
+  float wgt[2];
+  wanted_ranks(n, alpha, r, wgt);
   unsigned* sel = ws + kCoarseBins + 64;
-  int64_t cum = 0;
-  int found = 0;
-  for (int b = 0; b < kCoarseBins && found < 4; ++b) {
-    const int64_t next = cum + ws[b];
-    while (found < 4 && r[found] < next) {
-      sel[found] = (unsigned)b;
-      // rank of the wanted element inside this coarse bin
-      sel[4 + found] = (unsigned)(r[found] - cum);
-      ++found;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t next = cum + c[i];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      if (r[f] >= cum && r[f] < next) {
+        sel[f] = (unsigned)(4 * t + i);
+        sel[4 + f] = (unsigned)(r[f] - cum);  // rank of the wanted element inside this coarse bin
+      }
     }
     cum = next;
   }
@@ -404,7 +430,7 @@ extern "C" int mq_observer_percentile(const void* x, int64_t ldx, int64_t M, int
   if (blocks > cap) blocks = cap;
   pct_coarse_kernel<<<(int)blocks, 256, 0, st>>>((const __half*)x, ldx, M, C, ws);
   MQ_LAUNCH_CHECK("pct_coarse_kernel");
-  pct_select_kernel<<<1, 32, 0, st>>>(ws, n, alpha);
+  pct_select_kernel<<<1, 1024, 0, st>>>(ws, n, alpha);
   MQ_LAUNCH_CHECK("pct_select_kernel");
   pct_fine_kernel<<<(int)blocks, 256, 0, st>>>((const __half*)x, ldx, M, C, ws);
   MQ_LAUNCH_CHECK("pct_fine_kernel");
