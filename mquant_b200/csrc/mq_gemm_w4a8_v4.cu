@@ -46,15 +46,17 @@ constexpr int W_STAGE = BN * BK / 2;
 constexpr int SM_A = 0;
 constexpr int SM_B = SM_A + ASTAGES * A_STAGE;
 constexpr int SM_W = SM_B + BSTAGES * B_STAGE;
-constexpr int SM_EPI = SM_W + WSTAGES * W_STAGE;             // 8 warps x 2 buffers x (32 rows x 64 B)
-constexpr int SM_PARAM = SM_EPI + NUM_EPI_WARPS * 4096;      // s_w16 fp32[256], bias fp16[256], w0 fp16[256]
+// Output staging per epilogue warp: 32 rows x 64 B.  One buffer: a second one (tried) changes
+// nothing measurable -- the TMA store has read the tile long before the next 32 columns are
+// converted -- and would leave no room to re-align the dynamic window to 1024 bytes.
+constexpr int STG_BYTES = 2048;
+constexpr int SM_EPI = SM_W + WSTAGES * W_STAGE;
+constexpr int SM_PARAM = SM_EPI + NUM_EPI_WARPS * STG_BYTES;  // s_w16 fp32[256], bias fp16[256], w0 fp16[256]
 constexpr int SM_BAR = SM_PARAM + BN * 4 + 2 * BN * 2;
 constexpr int NUM_BARS = 2 * ASTAGES + 2 * BSTAGES + 2 * WSTAGES + 4;
 constexpr int SM_TMEMPTR = SM_BAR + NUM_BARS * 8;
 constexpr int SM_TOTAL = SM_TMEMPTR + 16;
-// No slack for re-aligning the base: the kernel has no static shared memory, so the dynamic
-// window starts 1024-byte aligned (checked at run time; SWIZZLE_128B needs it).
-constexpr int SM_ALLOC = SM_TOTAL;
+constexpr int SM_ALLOC = SM_TOTAL + 1024;  // slack to align the window to 1024 bytes (SWIZZLE_128B)
 static_assert(SM_ALLOC <= 227 * 1024, "shared memory budget");
 // s8 x s8 -> s32, K-major A and B, N = 256, M = 128
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
@@ -68,9 +70,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_out,
                     const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = smem_u32(smem_raw);
-  if (base & 1023u) __trap();
-  uint8_t* smem = smem_raw;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
   const uint32_t sA = base + SM_A, sB = base + SM_B, sW = base + SM_W;
   const uint32_t bar0 = base + SM_BAR;
   auto afull_bar = [&](int s) { return bar0 + 8u * s; };
@@ -293,8 +295,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     float* ps = reinterpret_cast<float*>(smem + SM_PARAM);
     __half* ps_bias = reinterpret_cast<__half*>(smem + SM_PARAM + BN * 4);
     __half* ps_w0 = ps_bias + BN;
-    const uint32_t stg0 = base + SM_EPI + (uint32_t)(warp - EPI_WARP0) * 4096u;
-    uint32_t sbuf = 0;  // staging buffer of the next store (two per warp)
+    const uint32_t stg = base + SM_EPI + (uint32_t)(warp - EPI_WARP0) * STG_BYTES;
     constexpr bool has_r1 = HAS_R1, has_bias = HAS_BIAS;
     int local = 0;
     uint32_t tile_phase = 0;
@@ -333,11 +334,9 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         auto process = [&](const uint32_t (&v)[32], int cc) {
           const int colb = col0 + cc * 32;
           if (p.dbg & 32u) return;  // probe: TMEM drain only
-          // the warp's staging tiles (two; 32 rows x 64 B, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk g of
+          // the warp's staging tile (32 rows x 64 B, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk g of
           // row r sits at g ^ ((r >> 1) & 3)) is free once the previous TMA store has read it
-          const uint32_t stg = stg0 + sbuf;
-          sbuf ^= 2048u;
-          if (lane == 0) bulk_wait_read_le1();  // the store issued two blocks ago has read this buffer
+          if (lane == 0) bulk_wait_read_all();  // the previous store has read the staging tile
           __syncwarp();
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
