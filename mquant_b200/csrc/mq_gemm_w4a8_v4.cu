@@ -344,7 +344,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // the two multiplications handle two columns per instruction (packed fp32: each half
             // rounds like the scalar op); the additions stay scalar -- ptxas contracts
             // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the .rn qualifiers, which changes 1 in
-            // 10^4 outputs by an fp16 ulp (test_gemm_tcgen05_matches_oracle caught it)
+            // 10^4 outputs by an fp16 ulp (caught by the GPU parity tests)
             float y[8];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
