@@ -240,7 +240,7 @@ w4a8_gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) 
         for (int kb = 0; kb < p.k_tiles; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint64_t adesc = make_kmajor_sw128_desc(sA + stage * A_STAGE);
             const uint64_t bdesc = make_kmajor_sw128_desc(sB + stage * C::B_STAGE);
 #pragma unroll

@@ -164,7 +164,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t tile_phase = 0;
     auto issue = [&](int h, int sa_, int sb_, int kb) {
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t adesc = make_kmajor_sw128_desc(sA + sa_ * A_STAGE + h * AH_STAGE);
         const uint64_t bdesc = make_kmajor_sw128_desc(sB + sb_ * B_STAGE);
         const uint32_t tmem_d = tmem_base + (uint32_t)(h * BN);
@@ -176,7 +176,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       __syncwarp();
     };
     auto commit = [&](uint32_t bar) {
-      if (lane == 0) umma_commit(bar);
+      if (elect_one()) umma_commit(bar);
       __syncwarp();
     };
     for (int t = unit; t < total_tiles; t += num_units, tile_phase ^= 1u) {

@@ -219,7 +219,7 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       mbar_wait(d2_empty(d2), d2ph ^ 1u);
       stamp(prm, lu, 3);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t lbo = (uint32_t)c.Kpad * 128u;  // between the two 64-j' segments of a tile
 #pragma unroll 1
         for (int mt = 0; mt < MT; ++mt) {

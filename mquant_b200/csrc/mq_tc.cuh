@@ -30,6 +30,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// One lane of a converged warp, chosen by the hardware.  Unlike `lane == 0` the compiler knows that
+// exactly one thread executes the guarded code: tcgen05 / TMA instructions (uniform-datapath
+// operands) are then emitted back to back instead of inside an ELECT + BRA.U.ANY loop each.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // ---- f32x2 helpers: sm_100 packed fp32 arithmetic, each half an ordinary round-to-nearest op
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
   uint64_t r;
