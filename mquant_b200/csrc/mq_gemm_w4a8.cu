@@ -373,10 +373,15 @@ extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4,
   // weight conversion shared by two M halves (default for large M); v2 = 128 x 256 tile, 8-warp
   // pipelined epilogue with staged stores (default below); 2cta = its cta_group::2 flavour (correct, but its TMA path currently
   // under-performs, profiles/README.md); v1 = this file's first-generation kernel.
-  // default: the 256 x 256 kernel once its tiles fill the machine 1.5 times (measured cross-over,
-  // profiles/README.md), else the 128 x 256 kernel
-  const int64_t tiles256 = ((M + 255) / 256) * (int64_t)p.n_tiles;
-  int kernel = 2 * tiles256 >= 3 * (int64_t)num_sms() ? 5 : 2;
+  // default: the cheaper of the 256 x 256 kernel (v4) and the 128 x 256 kernel (v2) under a
+  // wave model fitted to tools/latency.py (us per wave of one tile per SM: v2 0.506 K + 6.5,
+  // v4 0.60 K + 7.5, K in k-blocks; profiles/README.md): v2 only wins while it needs a single wave
+  const int64_t sms = num_sms();
+  const int64_t waves2 = (((M + 127) / 128) * (int64_t)p.n_tiles + sms - 1) / sms;
+  const int64_t waves4 = (((M + 255) / 256) * (int64_t)p.n_tiles + sms - 1) / sms;
+  const double cost2 = (double)waves2 * (0.506 * p.k_tiles + 6.5);
+  const double cost4 = (double)waves4 * (0.60 * p.k_tiles + 7.5);
+  int kernel = cost4 < cost2 ? 5 : 2;
   if (kenv) {
     if (kenv[0] == '2') kernel = 3;                         // "2cta"
     else if (kenv[0] == 'v' && kenv[1] == '1') kernel = 1;  // "v1"
