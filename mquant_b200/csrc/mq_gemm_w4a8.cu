@@ -311,6 +311,7 @@ extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4,
                                size_t workspace_bytes, void* stream) {
   using namespace mq;
   using namespace mq::gemm;
+  if (M == 0) return MQ_OK;  // empty batch: nothing to do (its tensors have null data pointers)
   MQ_REQUIRE(qa && w4 && s_a && s_w && out, "mq_w4a8_gemm: null pointer");
   MQ_REQUIRE(M >= 0 && N > 0 && K > 0, "mq_w4a8_gemm: bad shape (M=%lld N=%lld K=%lld)", (long long)M,
              (long long)N, (long long)K);

@@ -340,6 +340,7 @@ extern "C" int mq_hadamard_quant_i8(const void* x, int64_t ldx, int8_t* q, void*
                                     const void* hadk, int had_k, int64_t M, int n_in, int n, unsigned flags,
                                     void* stream) {
   using namespace mq;
+  if (M == 0) return MQ_OK;  // empty batch
   MQ_REQUIRE(x != nullptr && (q != nullptr || y_f16 != nullptr), "mq_hadamard_quant_i8: null pointer");
   MQ_REQUIRE(q == nullptr || scales != nullptr, "mq_hadamard_quant_i8: codes requested without scales");
   MQ_REQUIRE(M >= 0 && n > 0 && n_in > 0 && n_in <= n && n_in % 8 == 0 && ldx % 8 == 0 && ldx >= n_in,

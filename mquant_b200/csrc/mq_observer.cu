@@ -361,6 +361,7 @@ __global__ void pct_finish_kernel(const unsigned* __restrict__ ws, int64_t n, do
 extern "C" int mq_observer_minmax(const void* x, int64_t ldx, int64_t M, int C, int per_channel,
                                   float* minmax_io, void* stream) {
   using namespace mq;
+  if (M == 0) return MQ_OK;  // empty batch: statistics unchanged
   MQ_REQUIRE(x && minmax_io, "mq_observer_minmax: null pointer");
   MQ_REQUIRE(M >= 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldx >= C,
              "mq_observer_minmax: need C%%8==0 and ldx%%8==0 (C=%d ldx=%lld)", C, (long long)ldx);
@@ -389,6 +390,7 @@ extern "C" int mq_observer_minmax_msq(const void* x, int64_t ldx, int64_t M, int
                                       float* minmax_text_io, float* minmax_visual_io, unsigned* seen_io,
                                       void* stream) {
   using namespace mq;
+  if (M == 0) return MQ_OK;  // empty batch: statistics unchanged
   MQ_REQUIRE(x && modality && minmax_text_io && minmax_visual_io && seen_io, "mq_observer_minmax_msq: null pointer");
   MQ_REQUIRE(M >= 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldx >= C,
              "mq_observer_minmax_msq: need C%%8==0 and ldx%%8==0 (C=%d ldx=%lld)", C, (long long)ldx);

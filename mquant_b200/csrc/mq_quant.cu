@@ -169,6 +169,7 @@ static int grid_for(int64_t work_items, int threads, int per_sm) {
 extern "C" int mq_act_quant_i8(const void* x, int64_t ldx, int8_t* q, float* srow_out, void* x0_out,
                                const uint8_t* modality, const float* scales, int64_t M, int n_in,
                                int n_out, unsigned flags, void* stream) {
+  if (M == 0) return MQ_OK;  // empty batch
   MQ_REQUIRE(x && q && scales, "mq_act_quant_i8: null pointer");
   MQ_REQUIRE(M >= 0 && n_in > 0 && n_out >= n_in, "mq_act_quant_i8: bad shape M=%lld n_in=%d n_out=%d",
              (long long)M, n_in, n_out);
@@ -191,6 +192,7 @@ extern "C" int mq_act_quant_i8(const void* x, int64_t ldx, int8_t* q, float* sro
 extern "C" int mq_act_fake_quant_f16(const void* x, int64_t ldx, void* y, int64_t ldy,
                                      const uint8_t* modality, const float* scales, int scale_mode,
                                      int bits, int64_t M, int C, void* stream) {
+  if (M == 0) return MQ_OK;  // empty batch
   MQ_REQUIRE(x && y && scales, "mq_act_fake_quant_f16: null pointer");
   MQ_REQUIRE(M >= 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C,
              "mq_act_fake_quant_f16: need C%%8==0 and 8-element aligned strides (C=%d)", C);
@@ -213,6 +215,7 @@ extern "C" int mq_act_fake_quant_f16(const void* x, int64_t ldx, void* y, int64_
 
 extern "C" int mq_act_quant_i8_dynamic(const void* x, int64_t ldx, int8_t* q, float* srow_out, int64_t M,
                                        int n_in, int n_out, float clip_ratio, void* stream) {
+  if (M == 0) return MQ_OK;  // empty batch
   MQ_REQUIRE(x && q && srow_out, "mq_act_quant_i8_dynamic: null pointer");
   MQ_REQUIRE(M >= 0 && n_in > 0 && n_out >= n_in && n_in % 8 == 0 && n_out % 16 == 0 && ldx % 8 == 0 &&
                  ldx >= n_in,

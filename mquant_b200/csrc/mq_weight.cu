@@ -230,6 +230,7 @@ extern "C" int mq_w4a8_gemm_simt(const int8_t* qa, int64_t lda, const uint8_t* w
                                  const void* w0, void* out, int64_t ldo, int64_t M, int64_t N, int64_t K,
                                  void* stream) {
   using namespace mq;
+  if (M == 0) return MQ_OK;  // empty batch
   MQ_REQUIRE(qa && w4 && s_a && s_w && out, "mq_w4a8_gemm_simt: null pointer");
   MQ_REQUIRE(M >= 0 && N > 0 && K > 0 && K % kW4TileK == 0 && lda >= K && ldo >= N,
              "mq_w4a8_gemm_simt: bad shape (M=%lld N=%lld K=%lld)", (long long)M, (long long)N, (long long)K);

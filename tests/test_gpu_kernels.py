@@ -343,6 +343,36 @@ def test_matmul_hadU_cuda_api(ops, golden):
     np.testing.assert_allclose(host(y), ref, atol=2e-5)
 
 
+def test_empty_batches_are_noops(ops):
+    """M = 0 (an empty torch tensor has a null data pointer): every entry point returns without
+    touching its outputs, like the reference on an empty batch."""
+    from mquant_b200 import hadamard_utils as hu
+
+    x = torch.empty((0, 4096), dtype=torch.float16, device="cuda")
+    scales = ops.make_scales(0.1, 0.2, "cuda")
+    mod = torch.empty((0,), dtype=torch.uint8, device="cuda")
+    q, srow, _ = ops.act_quant_i8(x, scales, mod, want_row_scales=True)
+    assert q.shape == (0, 4096)
+    assert ops.act_fake_quant(x, scales, mod).shape == (0, 4096)
+    st = torch.tensor([-1.0, 2.0], device="cuda")
+    ops.observer_minmax(x, st)
+    assert host(st).tolist() == [-1.0, 2.0]
+    st_v = torch.zeros(2, device="cuda")
+    seen = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ops.observer_minmax_msq(x, mod, st, st_v, seen)
+    assert host(seen).tolist() == [0, 0] and host(st).tolist() == [-1.0, 2.0]
+    r = ops.hadamard(x, n=4096, scales=scales, want_codes=True, want_f16=True)
+    assert r["q"].shape == (0, 4096) and r["y"].shape == (0, 4096)
+    x2 = torch.empty((0, 11008), dtype=torch.float16, device="cuda")
+    r = ops.hadamard(x2, had_k=172, hadk=hu.hadK_device(172, "cuda"), n=11008, scales=scales, want_codes=True, want_f16=False)
+    assert r["q"].shape == (0, 11008)
+    w4 = ops.pack_w4(torch.zeros((256, 128), dtype=torch.int8, device="cuda"))
+    out = ops.w4a8_gemm(torch.empty((0, 128), dtype=torch.int8, device="cuda"), w4, torch.ones(1, device="cuda"),
+                        torch.ones(256, device="cuda"), 256)
+    assert out.shape == (0, 256)
+    torch.cuda.synchronize()
+
+
 def test_observer_minmax_msq_fused(ops):
     """One pass for both modalities (mq_observer_minmax_msq) == two MinmaxObservers on x[~mask] and
     x[mask]; row counts tell which modality occurred."""
