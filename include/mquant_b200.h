@@ -166,12 +166,17 @@ int mq_w4a8_gemm(const int8_t* qa, int64_t lda, const uint8_t* w4, const float* 
                  const void* w0, void* out, int64_t ldo, int64_t M, int64_t N, int64_t K,
                  void* stream);
 
-/* Same contract with an optional workspace.  For M <= 16 (decode) a workspace of at least
- * mq_w4a8_gemm_workspace_bytes(M, N, K) bytes selects the weight-streaming split-K kernel (the
- * layer is bound by the N*K/2-byte weight stream there, not by the tensor pipe).  The workspace
- * must be ZERO before its first use; the kernel leaves it zero again, so it can be reused by every
- * later call on the same stream without clearing.  workspace == NULL or M > 16: identical to
- * mq_w4a8_gemm.  mq_w4a8_gemm_workspace_bytes returns 0 when no workspace is useful. */
+/* Same contract with an optional workspace of at least mq_w4a8_gemm_workspace_bytes(M, N, K)
+ * bytes, which enables the kernels that split K across CTAs and merge int32 partial sums
+ * (integer adds: exact and order independent, results stay bit-identical):
+ *   M <= 8 (<= 16 for N < 8192)  decode: weight-streaming dp4a kernel, bound by the N*K/2-byte
+ *                                weight stream rather than by the tensor pipe;
+ *   up to ~1000 rows             the tcgen05 kernel with K slices, while M/128 * N/256 tiles are
+ *                                too few to fill the SMs.
+ * The workspace must be ZERO before its first use; every call leaves it zero again, so one buffer
+ * can be reused by all later calls on the same stream without clearing (calls on different
+ * streams need their own).  workspace == NULL: identical to mq_w4a8_gemm.
+ * mq_w4a8_gemm_workspace_bytes returns 0 when no workspace is useful for the shape. */
 size_t mq_w4a8_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4, const float* s_a,
                     int s_a_per_row, const float* s_w, const void* bias, const void* x0,
