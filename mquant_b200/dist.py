@@ -79,8 +79,11 @@ def merge_calibration(model, group=None, channels_hint=None):
     for _, layer in find_qlayers(model, layers=[ActQuantWrapper]).items():
         q = layer.quantizer
         if getattr(q, "static", False) and getattr(q, "msq", False) and getattr(q, "_seen", None) is None:
-            q._seen_host = (int(q.observer.max_val is not None),
-                            int(q.observer_visual is not None and q.observer_visual.max_val is not None))
+            def seen(o):
+                if o is None:
+                    return 0
+                return int((o.state if hasattr(o, "state") else o.max_val) is not None)
+            q._seen_host = (seen(q.observer), seen(q.observer_visual))
     distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     dev = None
     for _, o in obs:
@@ -117,7 +120,7 @@ def merge_calibration(model, group=None, channels_hint=None):
     # the scales were last derived from rank-local statistics: recompute them from the merged ones
     for _, layer in find_qlayers(model, layers=[ActQuantWrapper]).items():
         q = layer.quantizer
-        if getattr(q, "static", False) and (q.observer.max_val is not None or
-                                            (q.msq and q.observer_visual.max_val is not None)):
+        if getattr(q, "static", False) and (getattr(q.observer, "state", None) is not None or
+                                            (q.msq and getattr(q.observer_visual, "state", None) is not None)):
             q.update_quantization_params()
     return len(live)

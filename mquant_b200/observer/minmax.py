@@ -19,6 +19,31 @@ class MinmaxObserver(BaseObserver):
         self._dtype = None     # dtype of the observed activations (statistics keep it)
         self._channels = None
 
+    # min_val / max_val (the reference's attributes) are VIEWS of the device buffer, materialised
+    # when somebody reads them: an update is one kernel launch, not one launch plus four tiny
+    # slice/convert kernels (calibration of ~1000-token samples is launch bound).
+    @property
+    def min_val(self):
+        if self.state is None:
+            return None
+        return (self.state[:self._channels] if self._per_channel() else self.state[0]).to(self._dtype)
+
+    @min_val.setter
+    def min_val(self, v):  # BaseObserver.__init__ assigns None
+        if v is not None:
+            raise AttributeError("MinmaxObserver.min_val is derived from .state")
+
+    @property
+    def max_val(self):
+        if self.state is None:
+            return None
+        return (self.state[self._channels:] if self._per_channel() else self.state[1]).to(self._dtype)
+
+    @max_val.setter
+    def max_val(self, v):
+        if v is not None:
+            raise AttributeError("MinmaxObserver.max_val is derived from .state")
+
     def _per_channel(self):
         return self.calibration_mode != "layer_wise"
 
@@ -34,16 +59,10 @@ class MinmaxObserver(BaseObserver):
             self.state = torch.zeros(n, dtype=torch.float32, device=v.device)
             self._dtype, self._channels = v.dtype, C
         ops.observer_minmax(v, self.state, per_channel=self._per_channel())
-        self._refresh()
 
     def _refresh(self):
-        if self._per_channel():
-            C = self._channels
-            self.min_val = self.state[:C].to(self._dtype)
-            self.max_val = self.state[C:].to(self._dtype)
-        else:
-            self.min_val = self.state[0].to(self._dtype)
-            self.max_val = self.state[1].to(self._dtype)
+        """Kept for callers that modified .state directly (mquant_b200.dist): nothing to do, the
+        views are derived on access."""
 
     def get_quantization_params(self, *args, **kwargs):
         return self._params_from_minmax()

@@ -97,6 +97,12 @@ def unpack_i4(x: torch.Tensor):
 
 # ---- activation quantizer ---------------------------------------------------------------------
 
+def _observed(observer):
+    """Has this observer seen data?  (Without materialising the statistics.)"""
+    state = getattr(observer, "state", None)
+    return state is not None if hasattr(observer, "state") else observer.max_val is not None
+
+
 class ActQuantizer(torch.nn.Module):
     """Reference quant_utils.py:97-268."""
 
@@ -160,8 +166,6 @@ class ActQuantizer(torch.nn.Module):
             if getattr(self, "_seen", None) is None:
                 self._seen = torch.zeros(2, dtype=torch.int32, device=x.device)
             ops.observer_minmax_msq(x2, mod, self.observer.state, self.observer_visual.state, self._seen)
-            self.observer._refresh()
-            self.observer_visual._refresh()
             return
         vis = mod.bool()
         if bool((~vis).any()):
@@ -178,8 +182,8 @@ class ActQuantizer(torch.nn.Module):
     def _seen_kinds(self):
         """(text seen, visual seen).  The fused observer counts rows on the device: one read here,
         when the parameters are derived, instead of one per observed batch."""
-        has_t = self.observer.max_val is not None
-        has_v = self.msq and self.observer_visual.max_val is not None
+        has_t = _observed(self.observer)
+        has_v = self.msq and _observed(self.observer_visual)
         seen = getattr(self, "_seen", None)
         if seen is not None:
             n_t, n_v = seen.tolist()
