@@ -46,18 +46,25 @@ constexpr int W_STAGE = BN * BK / 2;
 constexpr int SM_A = 0;
 constexpr int SM_B = SM_A + ASTAGES * A_STAGE;
 constexpr int SM_W = SM_B + BSTAGES * B_STAGE;
-// Output staging per epilogue warp: 32 rows x 64 B.  One buffer: a second one (tried) changes
-// nothing measurable -- the TMA store has read the tile long before the next 32 columns are
-// converted -- and would leave no room to re-align the dynamic window to 1024 bytes.
+// Output staging per epilogue warp: 32 rows x 64 B, two buffers (warp sampling: with one buffer
+// 14 % of the active epilogue time waits for the previous TMA store to have read it).  The
+// bias / w0 parameter arrays exist only in the variants that use them; with both there is room
+// for one staging buffer only.
 constexpr int STG_BYTES = 2048;
 constexpr int SM_EPI = SM_W + WSTAGES * W_STAGE;
-constexpr int SM_PARAM = SM_EPI + NUM_EPI_WARPS * STG_BYTES;  // s_w16 fp32[256], bias fp16[256], w0 fp16[256]
-constexpr int SM_BAR = SM_PARAM + BN * 4 + 2 * BN * 2;
 constexpr int NUM_BARS = 2 * ASTAGES + 2 * BSTAGES + 2 * WSTAGES + 4;
-constexpr int SM_TMEMPTR = SM_BAR + NUM_BARS * 8;
-constexpr int SM_TOTAL = SM_TMEMPTR + 16;
-constexpr int SM_ALLOC = SM_TOTAL + 1024;  // slack to align the window to 1024 bytes (SWIZZLE_128B)
-static_assert(SM_ALLOC <= 227 * 1024, "shared memory budget");
+template <bool HAS_R1, bool HAS_BIAS>
+struct Lay {
+  static constexpr int STG_BUFS = (HAS_R1 && HAS_BIAS) ? 1 : 2;
+  static constexpr int SM_PARAM = SM_EPI + NUM_EPI_WARPS * STG_BUFS * STG_BYTES;  // s_w16 fp32[256]
+  static constexpr int SM_BIAS = SM_PARAM + BN * 4;                               // bias fp16[256]
+  static constexpr int SM_W0 = SM_BIAS + (HAS_BIAS ? BN * 2 : 0);                 // w0 fp16[256]
+  static constexpr int SM_BAR = SM_W0 + (HAS_R1 ? BN * 2 : 0);
+  static constexpr int SM_TMEMPTR = SM_BAR + NUM_BARS * 8;
+  static constexpr int SM_TOTAL = SM_TMEMPTR + 16;
+  static constexpr int SM_ALLOC = SM_TOTAL + 1024;  // slack to align the window to 1024 bytes (SWIZZLE_128B)
+  static_assert(SM_ALLOC <= 227 * 1024, "shared memory budget");
+};
 // s8 x s8 -> s32, K-major A and B, N = 256, M = 128
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(BMH >> 4) << 24);
@@ -69,6 +76,8 @@ template <bool HAS_R1, bool HAS_BIAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_out,
                     const Params p) {
+  using L = Lay<HAS_R1, HAS_BIAS>;
+  constexpr int SM_BAR = L::SM_BAR, SM_TMEMPTR = L::SM_TMEMPTR, SM_PARAM = L::SM_PARAM;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -293,9 +302,10 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int chalf = (warp - EPI_WARP0) >> 2;
     const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
     float* ps = reinterpret_cast<float*>(smem + SM_PARAM);
-    __half* ps_bias = reinterpret_cast<__half*>(smem + SM_PARAM + BN * 4);
-    __half* ps_w0 = ps_bias + BN;
-    const uint32_t stg = base + SM_EPI + (uint32_t)(warp - EPI_WARP0) * STG_BYTES;
+    __half* ps_bias = reinterpret_cast<__half*>(smem + L::SM_BIAS);
+    __half* ps_w0 = reinterpret_cast<__half*>(smem + L::SM_W0);
+    const uint32_t stg0 = base + SM_EPI + (uint32_t)(warp - EPI_WARP0) * (L::STG_BUFS * STG_BYTES);
+    uint32_t sbuf = 0;
     constexpr bool has_r1 = HAS_R1, has_bias = HAS_BIAS;
     int local = 0;
     uint32_t tile_phase = 0;
@@ -336,11 +346,25 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (p.dbg & 32u) return;  // probe: TMEM drain only
           // the warp's staging tile (32 rows x 64 B, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk g of
           // row r sits at g ^ ((r >> 1) & 3)) is free once the previous TMA store has read it
-          if (lane == 0) bulk_wait_read_all();  // the previous store has read the staging tile
+          const uint32_t stg = stg0 + sbuf;
+          if (L::STG_BUFS == 2) {
+            sbuf ^= STG_BYTES;
+            if (lane == 0) bulk_wait_read_le1();  // the store issued two blocks ago has read this buffer
+          } else {
+            if (lane == 0) bulk_wait_read_all();  // the previous store has read the staging tile
+          }
           __syncwarp();
+          // s_w of the next 8 columns is fetched while the current 8 are computed (the sampled
+          // profile showed the multiplies waiting on these shared-memory loads)
+          float4 swa = *reinterpret_cast<const float4*>(ps + colb), swb = *reinterpret_cast<const float4*>(ps + colb + 4);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = colb + g * 8;
+            const float sw[8] = {swa.x, swa.y, swa.z, swa.w, swb.x, swb.y, swb.z, swb.w};
+            if (g < 3) {
+              swa = *reinterpret_cast<const float4*>(ps + col + 8);
+              swb = *reinterpret_cast<const float4*>(ps + col + 12);
+            }
             // the two multiplications handle two columns per instruction (packed fp32: each half
             // rounds like the scalar op); the additions stay scalar -- ptxas contracts
             // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 despite the .rn qualifiers, which changes 1 in
@@ -348,7 +372,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             float y[8];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
-              const uint64_t sc = f2_mul(sa2p, f2_pack(ps[col + e], ps[col + e + 1]));
+              const uint64_t sc = f2_mul(sa2p, f2_pack(sw[e], sw[e + 1]));
               f2_unpack(f2_mul(f2_pack((float)(int)v[g * 8 + e], (float)(int)v[g * 8 + e + 1]), sc), y[e], y[e + 1]);
               if (has_r1) {
                 const float2 w0f = __half22float2(*reinterpret_cast<const __half2*>(ps_w0 + col + e));
@@ -407,6 +431,7 @@ static int launch_variant(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out
                           cudaStream_t st) {
   using namespace v4;
   auto* kern = w4a8_gemm_v4_kernel<HAS_R1, HAS_BIAS>;
+  constexpr int SM_ALLOC = Lay<HAS_R1, HAS_BIAS>::SM_ALLOC;
   MQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
   kern<<<grid, NUM_THREADS, SM_ALLOC, st>>>(tmap_a, tmap_out, p);
   return MQ_OK;

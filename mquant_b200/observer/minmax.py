@@ -29,9 +29,8 @@ class MinmaxObserver(BaseObserver):
         return (self.state[:self._channels] if self._per_channel() else self.state[0]).to(self._dtype)
 
     @min_val.setter
-    def min_val(self, v):  # BaseObserver.__init__ assigns None
-        if v is not None:
-            raise AttributeError("MinmaxObserver.min_val is derived from .state")
+    def min_val(self, v):  # BaseObserver.__init__ assigns None; callers may install statistics
+        self._assign(v, 0)
 
     @property
     def max_val(self):
@@ -41,8 +40,21 @@ class MinmaxObserver(BaseObserver):
 
     @max_val.setter
     def max_val(self, v):
-        if v is not None:
-            raise AttributeError("MinmaxObserver.max_val is derived from .state")
+        self._assign(v, 1)
+
+    def _assign(self, v, which):
+        """Assignment to min_val / max_val (as the reference's plain attributes allow, e.g. to
+        restore saved statistics) writes through to the device buffer."""
+        if v is None:
+            return
+        v = torch.as_tensor(v)
+        C = v.numel()
+        if self.state is None:
+            n = 2 * C if self._per_channel() else 2
+            self.state = torch.zeros(n, dtype=torch.float32, device=v.device)
+            self._dtype, self._channels = v.dtype, C
+        half = self.state.numel() // 2
+        self.state[which * half:(which + 1) * half] = v.reshape(-1).to(self.state.device, torch.float32)
 
     def _per_channel(self):
         return self.calibration_mode != "layer_wise"
