@@ -289,7 +289,7 @@ def main():
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per
     # launch, averaged over the step's shape mix); only meaningful for the default workload
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1d_gemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1e_gemm_traffic.json")
     if os.path.exists(tpath) and a.tokens == 16384:
         traffic = json.load(open(tpath)).get("avg_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "w4a8_gemm_v4_kernel", "achieved": achieved, "peak": peak,
