@@ -680,10 +680,18 @@ class _SiblingGroup:
         self._x = self._out = self._ver = None
         self._served = set()
 
+    @staticmethod
+    def _version_of(x):
+        try:
+            return x._version
+        except RuntimeError:  # inference tensors do not track versions: never share across calls
+            return None
+
     @torch.no_grad()
     def forward(self, member, x):
         idx = self.members.index(member)
-        hit = (self._x is x and self._ver == x._version and idx not in self._served)
+        ver = self._version_of(x)
+        hit = (ver is not None and self._x is x and self._ver == ver and idx not in self._served)
         if not hit:
             w = self.first
             qz = w.quantizer.quantizer
@@ -694,7 +702,7 @@ class _SiblingGroup:
                                           want_row_scales=modality is not None)
             s_a = srow if modality is not None else scales[0:1]
             self._out = ops.w4a8_gemm(q, self.w4, s_a, self.s_w, self.N, bias=self.bias)
-            self._x, self._ver, self._served = x, x._version, set()
+            self._x, self._ver, self._served = x, ver, set()
         self._served.add(idx)
         N = member._packed["N"]
         y = self._out[:, self.offsets[idx]:self.offsets[idx] + N].reshape(*x.shape[:-1], N)
