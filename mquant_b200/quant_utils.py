@@ -156,13 +156,18 @@ class ActQuantizer(torch.nn.Module):
             self.observer.update(x)
             return
         x2 = x.reshape(-1, x.shape[-1])
+        if x2.dtype != torch.float16 and x2.is_cuda and x2.dtype in (torch.bfloat16, torch.float32):
+            for o in (self.observer, self.observer_visual):
+                if getattr(o, "_dtype", None) is None and hasattr(o, "_dtype"):
+                    o._dtype = x.dtype  # statistics (and the scale) keep the activation dtype
+            x2 = x2.clamp(-65504.0, 65504.0).to(torch.float16)
         if self._fused_msq_ok(x2):
             # one kernel: both modalities' min/max and the row counts of either kind, no gathers
             # and no device round trip (mq_observer_minmax_msq)
             for o in (self.observer, self.observer_visual):
                 if o.state is None:
                     o.state = torch.zeros(2, dtype=torch.float32, device=x.device)
-                    o._dtype, o._channels = x.dtype, x2.shape[-1]
+                    o._dtype, o._channels = (o._dtype or x.dtype), x2.shape[-1]
             if getattr(self, "_seen", None) is None:
                 self._seen = torch.zeros(2, dtype=torch.int32, device=x.device)
             ops.observer_minmax_msq(x2, mod, self.observer.state, self.observer_visual.state, self._seen)
@@ -364,8 +369,9 @@ class ActQuantWrapper(torch.nn.Module):
         if self.online_full_had:
             n = self.pad_to or x.shape[-1]
             hk = hadamard_utils.hadK_device(self.K, x.device) if self.K > 1 else None
-            y = ops.hadamard(x, had_k=self.K, hadk=hk, n=n, fp32_had=self.fp32_had)["y"]
-            return y.reshape(*x.shape[:-1], n)
+            xh = x if x.dtype == torch.float16 else x.clamp(-65504.0, 65504.0).to(torch.float16)
+            y = ops.hadamard(xh, had_k=self.K, hadk=hk, n=n, fp32_had=self.fp32_had)["y"]
+            return y.reshape(*x.shape[:-1], n).to(x.dtype)
         if self.online_partial_had:
             raise NotImplementedError("online_partial_had is never enabled by the reference drivers")
         if self.pad_to and self.pad_to > x.shape[-1]:
@@ -375,9 +381,12 @@ class ActQuantWrapper(torch.nn.Module):
     def forward(self, x):
         x_dtype = x.dtype
         q = self.quantizer
-        if (self.real_quant and q.static and q.quant and not q.calibrate
-                and x.dtype == torch.float16 and self.out_quantizer.bits >= 16):
-            return self._forward_real(x)
+        if (self.real_quant and q.static and q.quant and not q.calibrate and self.out_quantizer.bits >= 16):
+            if x.dtype == torch.float16:
+                return self._forward_real(x)
+            if x.dtype in (torch.bfloat16, torch.float32):
+                # the integer path computes in fp16 in / fp16 out (exact conversion of in-range bf16)
+                return self._forward_real(x.clamp(-65504.0, 65504.0).to(torch.float16)).to(x_dtype)
 
         x = self._rotate(x)
         if self.split:

@@ -261,3 +261,47 @@ def test_sibling_fusion_is_bit_identical(qu):
         v1 = blk_f["attn_v_proj"](h.clone())
         assert torch.equal(v1.contiguous().view(torch.int16), blk_p["attn_v_proj"](h).view(torch.int16))
         assert q1.shape == (300, 4096)
+
+
+@torch.no_grad()
+def test_bf16_activations(qu):
+    """InternVL2 / Qwen2-VL run in bf16.  The kernels take fp16 (an in-range bf16 value converts
+    exactly), statistics and scales stay in bf16 like the reference's, the fake-quant output is
+    rounded into bf16 with the reference's expression, the integer path returns bf16."""
+    from mquant_b200 import msq
+
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(512, 256, bias=True).to(torch.bfloat16).cuda()
+    w = qu.ActQuantWrapper(lin)
+    wq = qu.WeightQuantizer()
+    wq.configure(4, perchannel=True, sym=True, mse=False)
+    wq.find_params(lin.weight.data)
+    lin.weight.data = wq.quantize(lin.weight.data).to(torch.bfloat16)
+    w.quantizer.configure(bits=8, sym=True, static=True, observer_type="minmax", msq=True)
+    x = (torch.randn(2, 40, 512, device="cuda") * 2).to(torch.bfloat16)
+    mask = torch.zeros(80, dtype=torch.uint8, device="cuda")
+    mask[5:30] = 1
+    args = type("A", (), {"skip_names": []})()
+    with msq.modality_context(mask):
+        qu.calibrate_static(w, args, [x])
+        qz = w.quantizer.quantizer
+        assert qz.scale.dtype == torch.bfloat16 and qz.scale_visual.dtype == torch.bfloat16
+        # scales = the reference's formula evaluated in bf16 on the two token groups
+        x2 = x.reshape(-1, 512)
+        for sel, sc in ((mask == 0, qz.scale), (mask != 0, qz.scale_visual)):
+            mx = torch.clamp(x2[sel.bool()].max(), min=0).cpu()
+            mn = torch.clamp(x2[sel.bool()].min(), max=0).cpu()
+            want = torch.max(torch.abs(mn / -128), torch.abs(mx / 127)).clamp(min=torch.finfo(torch.float32).eps)
+            assert torch.equal(sc.cpu(), want), (sc, want)
+        y_fake = w(x.clone())
+        assert y_fake.dtype == torch.bfloat16
+        # fake-quant activations, reference expression
+        s_tok = torch.where(mask.bool(), qz.scale_visual.float().cuda(), qz.scale.float().cuda())[:, None]
+        xq = (torch.clamp(torch.round(x2.float() / s_tok), -128, 127) * s_tok).to(torch.bfloat16)
+        want = torch.nn.functional.linear(xq, lin.weight, lin.bias).reshape(2, 40, 256)
+        assert torch.equal(y_fake, want)
+        w.freeze(wq.scale)
+        y_real = w(x.clone())
+    assert y_real.dtype == torch.bfloat16
+    cos = torch.nn.functional.cosine_similarity(y_real.float().flatten(), y_fake.float().flatten(), dim=0)
+    assert cos > 0.9995, float(cos)
