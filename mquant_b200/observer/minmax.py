@@ -70,8 +70,8 @@ class MinmaxObserver(BaseObserver):
             n = 2 * C if self._per_channel() else 2
             self.state = torch.zeros(n, dtype=torch.float32, device=v.device)
             self._dtype, self._channels = v.dtype, C
-        if v.dtype != torch.float16:
-            # bf16 / fp32 statistics: max/min commute with the (monotone, in-range exact) conversion;
+        if v.dtype == torch.bfloat16:
+            # bf16 statistics: max/min commute with the (monotone, in-range exact) conversion;
             # _dtype keeps the input dtype so that the scale is derived in it, as the reference does
             v = v.clamp(-65504.0, 65504.0).to(torch.float16)
         ops.observer_minmax(v, self.state, per_channel=self._per_channel())

@@ -156,7 +156,7 @@ class ActQuantizer(torch.nn.Module):
             self.observer.update(x)
             return
         x2 = x.reshape(-1, x.shape[-1])
-        if x2.dtype != torch.float16 and x2.is_cuda and x2.dtype in (torch.bfloat16, torch.float32):
+        if x2.is_cuda and x2.dtype == torch.bfloat16:
             for o in (self.observer, self.observer_visual):
                 if getattr(o, "_dtype", None) is None and hasattr(o, "_dtype"):
                     o._dtype = x.dtype  # statistics (and the scale) keep the activation dtype
@@ -369,6 +369,8 @@ class ActQuantWrapper(torch.nn.Module):
         if self.online_full_had:
             n = self.pad_to or x.shape[-1]
             hk = hadamard_utils.hadK_device(self.K, x.device) if self.K > 1 else None
+            if x.dtype not in (torch.float16, torch.bfloat16):
+                raise NotImplementedError("online Hadamard: fp16 / bf16 activations only")
             xh = x if x.dtype == torch.float16 else x.clamp(-65504.0, 65504.0).to(torch.float16)
             y = ops.hadamard(xh, had_k=self.K, hadk=hk, n=n, fp32_had=self.fp32_had)["y"]
             return y.reshape(*x.shape[:-1], n).to(x.dtype)
@@ -384,7 +386,7 @@ class ActQuantWrapper(torch.nn.Module):
         if (self.real_quant and q.static and q.quant and not q.calibrate and self.out_quantizer.bits >= 16):
             if x.dtype == torch.float16:
                 return self._forward_real(x)
-            if x.dtype in (torch.bfloat16, torch.float32):
+            if x.dtype == torch.bfloat16:
                 # the integer path computes in fp16 in / fp16 out (exact conversion of in-range bf16)
                 return self._forward_real(x.clamp(-65504.0, 65504.0).to(torch.float16)).to(x_dtype)
 

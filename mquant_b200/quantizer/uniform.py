@@ -53,6 +53,8 @@ class UniformQuantizer(BaseQuantizer):
         self._check_symmetric()
         if self.bit_type.bits != 8 or self.per_channel:
             raise NotImplementedError("integer codes are produced for per-tensor INT8 only")
+        if inputs.dtype not in (torch.float16, torch.bfloat16):
+            raise NotImplementedError("integer codes: fp16 / bf16 activations only")
         x = inputs if inputs.dtype == torch.float16 else inputs.clamp(-65504.0, 65504.0).to(torch.float16)
         q, _, _ = ops.act_quant_i8(x, self.device_scales(x.device), modality, want_row_scales=False)
         return q.reshape(inputs.shape)
@@ -63,20 +65,22 @@ class UniformQuantizer(BaseQuantizer):
 
     def forward(self, inputs, modality=None):
         self._check_symmetric()
+        if inputs.dtype == torch.bfloat16:
+            return self._forward_bf16(inputs, modality)
         if inputs.dtype != torch.float16:
-            return self._forward_other_dtype(inputs, modality)
+            raise NotImplementedError("mquant_b200 quantises fp16 / bf16 activations (fp32 does not convert exactly)")
         return ops.act_fake_quant(inputs, self.device_scales(inputs.device), modality,
                                   bits=self.bit_type.bits, per_channel=self.per_channel)
 
-    def _forward_other_dtype(self, inputs, modality):
-        """bf16 / fp32 activations (InternVL2 and Qwen2-VL run in bf16).  The kernels take fp16; a
+    def _forward_bf16(self, inputs, modality):
+        """bf16 activations (InternVL2 and Qwen2-VL run in bf16).  The kernels take fp16; a
         bf16 value converts to fp16 EXACTLY while 2^-14 <= |x| <= 65504, so the INT8 codes are the
         reference's; the dequantisation ``(q * scale).to(x.dtype)`` is then done with the
         reference's own expression (uniform.py:34-43) to get its rounding into the input dtype.
         Values beyond +-65504 saturate (they have code +-127/-128 for every sane scale), values
         below 2^-14 lose bits that cannot reach the code unless scale < 2^-13."""
         if self.bit_type.bits != 8 or self.per_channel:
-            raise NotImplementedError("non-fp16 activations: per-tensor INT8 only (cast the model to fp16 otherwise)")
+            raise NotImplementedError("bf16 activations: per-tensor INT8 only (cast the model to fp16 otherwise)")
         lim = 65504.0
         xh = inputs.clamp(-lim, lim).to(torch.float16)
         x2 = xh.reshape(-1, xh.shape[-1])
@@ -86,4 +90,7 @@ class UniformQuantizer(BaseQuantizer):
             y = q.float() * srow[:, None]
         else:
             y = q.float() * self.scale.to(inputs.device).float()
+        # torch.round keeps the sign of a tiny negative quotient: a zero code of a strictly negative
+        # input dequantises to -0.0 (x = -0.0 itself becomes +0.0 through "+ zero_point")
+        y = torch.where((q == 0) & (x2 < 0), torch.full_like(y, -0.0), y)
         return y.to(inputs.dtype).reshape(inputs.shape)

@@ -226,6 +226,30 @@ def main():
     y = q(x)
     np.savez_compressed(os.path.join(OUT, "dynamic.npz"), x=x.numpy(),
                         scale=q.scale[..., 0].reshape(-1).numpy(), y=y.numpy())
+    # ---------------------------------------------------------------- 8. bf16 activations
+    # (appended last so that the random stream of the cases above is unchanged)
+    # InternVL2 / Qwen2-VL run in bf16: statistics, scale and output stay bf16 in the reference;
+    # stored as uint16 bit patterns (numpy has no bf16)
+    q = qu.ActQuantizer()
+    q.configure(bits=8, sym=True, static=True, observer_type="minmax", calibration_mode="layer_wise")
+    calib = [rnd(2, 24, 192, dtype=torch.bfloat16) for _ in range(3)]
+    q.calibrate = True
+    for i, c in enumerate(calib):
+        if i == len(calib) - 1:
+            q.last_calibrate = True
+        q(c)
+    q.calibrate = False
+    q.quant = True
+    x = rnd(2, 40, 192, scale=4.0, dtype=torch.bfloat16)
+    x[0, 0, :8] = torch.tensor([0.0, -0.0, 60000, -60000, 1e-3, -1e-3, 0.5, -0.5]).to(torch.bfloat16)
+    y = q(x)
+
+    def bits(t):
+        return t.contiguous().view(torch.int16).numpy().view(np.uint16)
+
+    np.savez_compressed(os.path.join(OUT, "act_quant_bf16.npz"), calib=bits(torch.stack(calib)), x=bits(x),
+                        scale=bits(q.quantizer.scale.reshape(1)), codes=q.quantizer.quant(x.float()).numpy(),
+                        y=bits(y))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

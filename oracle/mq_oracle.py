@@ -157,6 +157,39 @@ def minmax_params(min_val, max_val, bits=8):
 
 
 # ----------------------------------------------------------------------------------
+# bf16 activations (InternVL2 / Qwen2-VL).  numpy has no bfloat16: values travel as uint16 bit
+# patterns; bf16 -> fp32 is exact (the pattern is the upper half of the fp32 word), fp32 -> bf16
+# rounds to nearest even on the dropped 16 bits (what torch's .to(bfloat16) does).
+# ----------------------------------------------------------------------------------
+def bf16_to_f32(bits):
+    return (np.asarray(bits, dtype=np.uint16).astype(np.uint32) << 16).view(F32)
+
+
+def f32_to_bf16_bits(x):
+    u = np.ascontiguousarray(np.asarray(x, dtype=F32)).view(np.uint32).astype(np.uint64)
+    r = (u + 0x7FFF + ((u >> 16) & 1)) >> 16  # round to nearest even (finite inputs)
+    return r.astype(np.uint16)
+
+
+def minmax_params_bf16(min_bits, max_bits, bits=8):
+    """minmax_params for bf16 statistics: every torch op on bf16 tensors computes in fp32 and
+    rounds the result to bf16 (minmax.py:41-46 evaluated in the dtype of the statistics)."""
+    qmin, qmax = int_bounds(bits)
+    rb = lambda v: bf16_to_f32(f32_to_bf16_bits(v))  # noqa: E731
+    a = np.abs(rb(bf16_to_f32(min_bits) / F32(qmin)))
+    b = np.abs(rb(bf16_to_f32(max_bits) / F32(qmax)))
+    scale = np.maximum(np.maximum(a, b), rb(np.asarray(np.finfo(np.float32).eps, dtype=F32)))
+    return f32_to_bf16_bits(scale)
+
+
+def act_fake_quant_bf16(x_bits, scale_bits, bits=8):
+    """BaseQuantizer.forward on bf16 activations: codes from the fp32 quotient, dequantised in
+    fp32, rounded into bf16 (base.py:44-50, uniform.py:28-43).  Returns (codes fp32, y bits)."""
+    codes = act_quant_codes(bf16_to_f32(x_bits), bf16_to_f32(scale_bits), 0, bits)
+    return codes, f32_to_bf16_bits(codes * bf16_to_f32(scale_bits))
+
+
+# ----------------------------------------------------------------------------------
 # PercentileObserver (fake_quant/observer/percentile.py:26-79)
 # ----------------------------------------------------------------------------------
 

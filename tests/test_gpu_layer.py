@@ -305,3 +305,33 @@ def test_bf16_activations(qu):
     assert y_real.dtype == torch.bfloat16
     cos = torch.nn.functional.cosine_similarity(y_real.float().flatten(), y_fake.float().flatten(), dim=0)
     assert cos > 0.9995, float(cos)
+
+
+@torch.no_grad()
+def test_bf16_quantizer_matches_reference_golden(qu, golden):
+    """ActQuantizer on bf16 activations against outputs of the reference itself (run in bf16 on the
+    CPU, tests/golden/act_quant_bf16.npz): scale, codes and fake-quant output bit-exact."""
+    g = golden("act_quant_bf16")
+
+    def bf16(bits):
+        return torch.from_numpy(bits.astype(np.int16)).view(torch.bfloat16).cuda()
+
+    q = qu.ActQuantizer()
+    q.configure(bits=8, sym=True, static=True, observer_type="minmax", calibration_mode="layer_wise")
+    calib = bf16(g["calib"])
+    q.calibrate = True
+    for i in range(calib.shape[0]):
+        if i == calib.shape[0] - 1:
+            q.last_calibrate = True
+        q(calib[i])
+    q.calibrate = False
+    q.quant = True
+    sc = q.quantizer.scale
+    assert sc.dtype == torch.bfloat16
+    assert np.array_equal(sc.reshape(1).cpu().view(torch.int16).numpy().view(np.uint16), g["scale"].reshape(-1))
+    x = bf16(g["x"])
+    y = q(x)
+    assert y.dtype == torch.bfloat16
+    assert np.array_equal(y.cpu().view(torch.int16).numpy().view(np.uint16), g["y"])
+    codes = q.quantizer.quant(x)
+    assert np.array_equal(codes.cpu().numpy().astype(np.float32), g["codes"])

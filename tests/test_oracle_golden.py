@@ -208,3 +208,16 @@ def test_torch_port_matches_reference(golden, tag):
     y = TP.qlinear_fake(x, W, b, torch.from_numpy(g[f"{tag}_act_scale"]), hk, K).numpy()
     ref = g[f"{tag}_y"].astype(np.float32)
     assert np.abs(y.astype(np.float32) - ref).max() <= 2.0 ** -9 * np.abs(ref).max() + 1e-3
+
+
+def test_bf16_activations_match_reference(golden):
+    """bf16 statistics, scale and fake-quant output (the reference run in bf16 on CPU)."""
+    g = golden("act_quant_bf16")
+    calib = O.bf16_to_f32(g["calib"])
+    mx = max(float(calib.max()), 0.0)
+    mn = min(float(calib.min()), 0.0)
+    scale = O.minmax_params_bf16(O.f32_to_bf16_bits(np.float32(mn)), O.f32_to_bf16_bits(np.float32(mx)))
+    assert np.array_equal(scale.reshape(-1), g["scale"].reshape(-1))
+    codes, y = O.act_fake_quant_bf16(g["x"], g["scale"].reshape(()))
+    assert np.array_equal(codes, g["codes"])
+    assert np.array_equal(y, g["y"])
