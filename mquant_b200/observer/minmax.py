@@ -69,7 +69,8 @@ class MinmaxObserver(BaseObserver):
         if self.state is None:
             n = 2 * C if self._per_channel() else 2
             self.state = torch.zeros(n, dtype=torch.float32, device=v.device)
-            self._dtype, self._channels = v.dtype, C
+            # (a caller that already converted bf16 activations has recorded their dtype)
+            self._dtype, self._channels = (self._dtype or v.dtype), C
         if v.dtype == torch.bfloat16:
             # bf16 statistics: max/min commute with the (monotone, in-range exact) conversion;
             # _dtype keeps the input dtype so that the scale is derived in it, as the reference does
