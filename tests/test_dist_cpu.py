@@ -69,3 +69,46 @@ def test_shard_indices_cover_everything():
     for world in (1, 2, 4, 8):
         got = sorted(i for r in range(world) for i in mqd.shard_indices(256, r, world))
         assert got == list(range(256))
+
+
+def _worker_model(rank, world, port, ret):
+    """merge_calibration on a wrapped model whose ranks saw different modalities: rank 0 only text
+    tokens, rank 1 text and visual tokens (statistics installed as the kernels would leave them)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mquant_b200 import dist as mqd, quant_utils as qu
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = torch.nn.Linear(16, 8)
+
+    net = Net()
+    qu.add_actquant(net)
+    q = net.fc.quantizer
+    q.configure(bits=8, sym=True, static=True, observer_type="minmax", msq=True)
+    text = {0: (-1.5, 2.0), 1: (-3.0, 1.0)}[rank]
+    q.observer.state = torch.tensor(text, dtype=torch.float32)
+    q.observer._dtype, q.observer._channels = torch.float16, 16
+    q._seen = torch.tensor([10, 0 if rank == 0 else 4], dtype=torch.int32)
+    if rank == 1:
+        q.observer_visual.state = torch.tensor([-8.0, 6.0], dtype=torch.float32)
+        q.observer_visual._dtype, q.observer_visual._channels = torch.float16, 16
+    n = mqd.merge_calibration(net)
+    qz = q.quantizer
+    ret[rank] = (n, float(qz.scale), None if qz.scale_visual is None else float(qz.scale_visual), q._seen.tolist())
+    dist.destroy_process_group()
+
+
+def test_merge_calibration_agrees_on_modalities_seen():
+    world = 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_model, args=(world, port, ret), nprocs=world, join=True)
+    # merged statistics: text (-3, 2), visual (-8, 6); both ranks derive both scales
+    s_text, _ = O.minmax_params(np.float16(-3.0), np.float16(2.0))
+    s_vis, _ = O.minmax_params(np.float16(-8.0), np.float16(6.0))
+    for r in range(world):
+        n, st, sv, seen = ret[r]
+        assert n == 2 and seen == [20, 4]
+        assert np.float16(st) == s_text and sv is not None and np.float16(sv) == s_vis

@@ -171,3 +171,37 @@ def test_compat_shim_resolves_fake_quant(built):
         assert quant_utils is built.quant_utils and fq is not None
     finally:
         sys.path.remove(os.path.join(ROOT, "compat"))
+
+
+def test_fuse_siblings_gating(built):
+    """fuse_siblings only groups wrappers for which sharing is exact (host logic; the packed
+    weights are stand-in byte buffers, nothing is launched)."""
+    import torch
+    from mquant_b200 import quant_utils as qu
+
+    def wrapper(n_out, scale=0.05, scale_v=0.1, k=256, had=False):
+        w = qu.ActQuantWrapper(torch.nn.Linear(k, n_out, bias=False))
+        w.quantizer.configure(bits=8, sym=True, static=True, observer_type="minmax", msq=scale_v is not None)
+        w.quantizer.quantizer.set_scales(torch.tensor(scale, dtype=torch.float16),
+                                         None if scale_v is None else torch.tensor(scale_v, dtype=torch.float16))
+        w._packed = {"w4": torch.zeros(n_out * k // 2, dtype=torch.uint8), "s_w": torch.ones(n_out), "w0": None,
+                     "bias": None, "N": n_out, "K": k, "Kp": k}
+        w.real_quant = True
+        w.online_full_had = had
+        return w
+
+    a, b, c = wrapper(512), wrapper(256), wrapper(104)
+    g = qu.fuse_siblings([a, b, c])          # ragged last member is fine
+    assert g is not None and g.N == 872 and g.offsets == [0, 512, 768] and a._group is g and c._group is g
+    assert g.w4.numel() == 872 * 256 // 2 and g.s_w.numel() == 872 and g.bias is None
+    assert qu.fuse_siblings([a, wrapper(256)]) is None                      # already grouped
+    assert qu.fuse_siblings([wrapper(104), wrapper(256)]) is None           # ragged member not last
+    assert qu.fuse_siblings([wrapper(256), wrapper(256, scale=0.06)]) is None   # different text scale
+    assert qu.fuse_siblings([wrapper(256), wrapper(256, scale_v=0.2)]) is None  # different visual scale
+    assert qu.fuse_siblings([wrapper(256), wrapper(256, scale_v=None)]) is None # MSQ vs not
+    assert qu.fuse_siblings([wrapper(256), wrapper(256, had=True)]) is None     # online rotation
+    assert qu.fuse_siblings([wrapper(256), wrapper(256, k=512)]) is None        # different K
+    assert qu.fuse_siblings([wrapper(256)]) is None
+    unfrozen = wrapper(256)
+    unfrozen.real_quant = False
+    assert qu.fuse_siblings([wrapper(256), unfrozen]) is None
