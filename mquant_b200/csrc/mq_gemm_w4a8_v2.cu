@@ -354,6 +354,16 @@ w4a8_gemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const Params p) 
       const bool has_r1 = p.x0 != nullptr, has_bias = p.bias != nullptr;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (p.dbg & 32u) {
+        // probe: no TMEM drain at all -- does the drain running beside the MMAs slow the main loop?
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (!TWO || cta == 0) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_cluster(tempty_leader + 8u * acc);
+        }
+        continue;
+      }
       const int col0 = chalf * (BN / 2);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + col0);
       uint32_t va[32], vb[32];
