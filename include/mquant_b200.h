@@ -100,6 +100,15 @@ int mq_hadamard_quant_i8(const void* x, int64_t ldx, int8_t* q, void* y_f16, flo
                          const void* hadk, int had_k, int64_t M, int n_in, int n,
                          unsigned flags, void* stream);
 
+/* The native seam of the reference, as it stands: fast_hadamard_transform.hadamard_transform(x,
+ * scale) (third-party CUDA extension; imported at fake_quant/hadamard_utils.py:2 and called at
+ * :118,:124,:168,:178,:188, quant_utils.py:351, rotation_utils.py:11):
+ *   y = fp16( fp32(x . H_n) * scale ),  H_n the Sylvester matrix, n a power of two in [64, 8192],
+ * fp32 butterflies, one rounding.  x: fp16 [M, n] row stride ldx; y: fp16 [M, n] contiguous
+ * (ldy == n).  compat/fast_hadamard_transform binds it under the original module name. */
+int mq_hadamard_transform_f16(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, int n,
+                              float scale, void* stream);
+
 /* ---- (c) observers ----------------------------------------------------------------------- */
 
 /* MinmaxObserver.update (minmax.py:13-28).  minmax_io is float[2] = {min, max} (layer_wise)

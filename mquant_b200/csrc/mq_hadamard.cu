@@ -335,34 +335,17 @@ static int launch_hadk(const HadArgs& a, cudaStream_t st) {
 
 }  // namespace mq
 
-extern "C" int mq_hadamard_quant_i8(const void* x, int64_t ldx, int8_t* q, void* y_f16, float* srow_out,
-                                    void* x0_out, const uint8_t* modality, const float* scales,
-                                    const void* hadk, int had_k, int64_t M, int n_in, int n, unsigned flags,
-                                    void* stream) {
-  using namespace mq;
-  if (M == 0) return MQ_OK;  // empty batch
-  MQ_REQUIRE(x != nullptr && (q != nullptr || y_f16 != nullptr), "mq_hadamard_quant_i8: null pointer");
-  MQ_REQUIRE(q == nullptr || scales != nullptr, "mq_hadamard_quant_i8: codes requested without scales");
-  MQ_REQUIRE(M >= 0 && n > 0 && n_in > 0 && n_in <= n && n_in % 8 == 0 && ldx % 8 == 0 && ldx >= n_in,
-             "mq_hadamard_quant_i8: bad shape (n_in=%d n=%d ldx=%lld)", n_in, n, (long long)ldx);
-  MQ_REQUIRE(had_k >= 1 && n % had_k == 0, "mq_hadamard_quant_i8: had_k=%d does not divide n=%d", had_k, n);
-  MQ_REQUIRE(aligned16(x) && aligned16(q) && aligned16(y_f16), "mq_hadamard_quant_i8: pointers must be 16-byte aligned");
-  MQ_REQUIRE(!(flags & MQ_FLAG_SPLIT) || (x0_out != nullptr && q != nullptr),
-             "mq_hadamard_quant_i8: MQ_FLAG_SPLIT needs q and x0_out");
-  const int P = n / had_k;
-  MQ_REQUIRE((P & (P - 1)) == 0, "mq_hadamard_quant_i8: n/had_k=%d is not a power of two", P);
-  MQ_REQUIRE(had_k == 1 || hadk != nullptr, "mq_hadamard_quant_i8: had_k>1 needs the hadK matrix");
-  if (M == 0) return MQ_OK;
+namespace mq {
+// shared by the two entry points: a.norm is the fp32 factor applied after the butterflies
+static int hadamard_dispatch(const HadArgs& a, cudaStream_t st) {
+  const int had_k = a.had_k;
+  const int P = a.n / had_k;
   int logp = 0;
   while ((1 << logp) < P) ++logp;
-  HadArgs a;
-  a.x = (const __half*)x; a.ldx = ldx; a.q = q; a.y = (__half*)y_f16; a.srow_out = srow_out;
-  a.x0_out = (__half*)x0_out; a.modality = modality; a.scales = scales; a.hadk = (const __half*)hadk;
-  a.had_k = had_k; a.M = M; a.n_in = n_in; a.n = n; a.flags = flags;
-  a.norm = 1.0f / sqrtf((float)n);  // float32(1/sqrt(n)): torch.tensor(n).sqrt() is fp32
-  cudaStream_t st = (cudaStream_t)stream;
   int rc = MQ_ERR_UNSUPPORTED;
-  if (had_k == 1) {
+  if (had_k == 1 && fwht_mma_supported(a)) {
+    rc = launch_fwht_mma(a, st);  // 16-point factors on the tensor pipe (mq_hadamard_mma.cu)
+  } else if (had_k == 1) {
     switch (logp) {
       case 6: rc = launch_warp<6>(a, st); break;
       case 7: rc = launch_warp<7>(a, st); break;
@@ -373,11 +356,9 @@ extern "C" int mq_hadamard_quant_i8(const void* x, int64_t ldx, int8_t* q, void*
       case 12: rc = launch_cta<12>(a, st); break;
       case 13: rc = launch_cta<13>(a, st); break;
       default:
-        set_error("mq_hadamard_quant_i8: power-of-two n=%d outside [64, 8192]", n);
+        set_error("mq_hadamard: power-of-two n=%d outside [64, 8192]", a.n);
         return MQ_ERR_UNSUPPORTED;
     }
-  } else if (const char* hk = getenv("MQ_HAD_KERNEL"); hk && hk[0] == 't' && hk[2] == '1' && hadk_tc_supported(a)) {
-    rc = launch_hadk_tc(a, st);  // "tc1": both Kronecker factors on tcgen05 (kept for comparison)
   } else if (hadk_tc2_supported(a) && (rc = launch_hadk_tc2(a, st)) != MQ_ERR_UNSUPPORTED) {
     // FWHT of the power-of-two factor in registers + hadK on tcgen05
   } else {
@@ -397,4 +378,48 @@ extern "C" int mq_hadamard_quant_i8(const void* x, int64_t ldx, int8_t* q, void*
   if (rc != MQ_OK) return rc;
   MQ_LAUNCH_CHECK("hadamard kernel");
   return MQ_OK;
+}
+}  // namespace mq
+
+extern "C" int mq_hadamard_quant_i8(const void* x, int64_t ldx, int8_t* q, void* y_f16, float* srow_out,
+                                    void* x0_out, const uint8_t* modality, const float* scales,
+                                    const void* hadk, int had_k, int64_t M, int n_in, int n, unsigned flags,
+                                    void* stream) {
+  using namespace mq;
+  if (M == 0) return MQ_OK;  // empty batch
+  MQ_REQUIRE(x != nullptr && (q != nullptr || y_f16 != nullptr), "mq_hadamard_quant_i8: null pointer");
+  MQ_REQUIRE(q == nullptr || scales != nullptr, "mq_hadamard_quant_i8: codes requested without scales");
+  MQ_REQUIRE(M >= 0 && n > 0 && n_in > 0 && n_in <= n && n_in % 8 == 0 && ldx % 8 == 0 && ldx >= n_in,
+             "mq_hadamard_quant_i8: bad shape (n_in=%d n=%d ldx=%lld)", n_in, n, (long long)ldx);
+  MQ_REQUIRE(had_k >= 1 && n % had_k == 0, "mq_hadamard_quant_i8: had_k=%d does not divide n=%d", had_k, n);
+  MQ_REQUIRE(aligned16(x) && aligned16(q) && aligned16(y_f16), "mq_hadamard_quant_i8: pointers must be 16-byte aligned");
+  MQ_REQUIRE(!(flags & MQ_FLAG_SPLIT) || (x0_out != nullptr && q != nullptr),
+             "mq_hadamard_quant_i8: MQ_FLAG_SPLIT needs q and x0_out");
+  const int P = n / had_k;
+  MQ_REQUIRE((P & (P - 1)) == 0, "mq_hadamard_quant_i8: n/had_k=%d is not a power of two", P);
+  MQ_REQUIRE(had_k == 1 || hadk != nullptr, "mq_hadamard_quant_i8: had_k>1 needs the hadK matrix");
+  HadArgs a;
+  a.x = (const __half*)x; a.ldx = ldx; a.q = q; a.y = (__half*)y_f16; a.srow_out = srow_out;
+  a.x0_out = (__half*)x0_out; a.modality = modality; a.scales = scales; a.hadk = (const __half*)hadk;
+  a.had_k = had_k; a.M = M; a.n_in = n_in; a.n = n; a.flags = flags;
+  a.norm = 1.0f / sqrtf((float)n);  // float32(1/sqrt(n)): torch.tensor(n).sqrt() is fp32
+  return hadamard_dispatch(a, (cudaStream_t)stream);
+}
+
+extern "C" int mq_hadamard_transform_f16(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t M, int n,
+                                         float scale, void* stream) {
+  using namespace mq;
+  if (M == 0) return MQ_OK;
+  MQ_REQUIRE(x != nullptr && y != nullptr, "mq_hadamard_transform_f16: null pointer");
+  MQ_REQUIRE(M >= 0 && n >= 64 && n <= 8192 && (n & (n - 1)) == 0,
+             "mq_hadamard_transform_f16: n=%d must be a power of two in [64, 8192]", n);
+  MQ_REQUIRE(ldx % 8 == 0 && ldx >= n && ldy == n, "mq_hadamard_transform_f16: bad strides (ldx=%lld ldy=%lld)",
+             (long long)ldx, (long long)ldy);
+  MQ_REQUIRE(aligned16(x) && aligned16(y), "mq_hadamard_transform_f16: pointers must be 16-byte aligned");
+  HadArgs a;
+  a.x = (const __half*)x; a.ldx = ldx; a.q = nullptr; a.y = (__half*)y; a.srow_out = nullptr;
+  a.x0_out = nullptr; a.modality = nullptr; a.scales = nullptr; a.hadk = nullptr;
+  a.had_k = 1; a.M = M; a.n_in = n; a.n = n; a.flags = 0;
+  a.norm = scale;
+  return hadamard_dispatch(a, (cudaStream_t)stream);
 }

@@ -30,4 +30,8 @@ int launch_hadk_tc(const HadArgs& a, cudaStream_t st);
 bool hadk_tc2_supported(const HadArgs& a);
 int launch_hadk_tc2(const HadArgs& a, cudaStream_t st);
 
+// mq_hadamard_mma.cu: power-of-two n in {1024, 2048, 4096}: 16-point factors on mma.sync, warp per token
+bool fwht_mma_supported(const HadArgs& a);
+int launch_fwht_mma(const HadArgs& a, cudaStream_t st);
+
 }  // namespace mq

@@ -11,8 +11,35 @@ from . import _lib
 from ._lib import MQ_FLAG_FP32_HAD, MQ_FLAG_SPLIT, check, lib
 
 
+import functools
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_device(fn):
+    """Run the op on the device (and that device's current stream) of its tensor arguments, not on
+    whatever device happens to be current: models sharded over several GPUs in one process
+    (device_map / split_model) call wrappers whose tensors live on cuda:1 while cuda:0 is current.
+    All tensor arguments must share one device."""
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for t in list(args) + list(kwargs.values()):
+            if torch.is_tensor(t) and t.is_cuda:
+                if dev is None:
+                    dev = t.device
+                elif t.device != dev:
+                    raise _lib.MQuantLibraryError(
+                        f"{fn.__name__}: tensor arguments on different devices ({dev} and {t.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapped
 
 
 def _need_cuda(*ts):
@@ -50,6 +77,7 @@ def make_scales(s_text, s_visual=None, device=None):
     return torch.stack(vals)
 
 
+@_on_device
 def act_quant_i8(x, scales, modality=None, n_out=None, split=False, want_row_scales=True):
     """mq_act_quant_i8.  x: [..., C] fp16.  Returns (codes int8 [M, n_out], s_row fp32 [M] | None,
     x0 fp16 [M] | None)."""
@@ -67,6 +95,7 @@ def act_quant_i8(x, scales, modality=None, n_out=None, split=False, want_row_sca
     return q, srow, x0
 
 
+@_on_device
 def act_fake_quant(x, scales, modality=None, bits=8, per_channel=False, out=None):
     """mq_act_fake_quant_f16: quant->dequant, same shape/dtype as x."""
     _need_cuda(x, scales, modality)
@@ -80,6 +109,7 @@ def act_fake_quant(x, scales, modality=None, bits=8, per_channel=False, out=None
     return y.reshape(x.shape)
 
 
+@_on_device
 def act_quant_i8_dynamic(x, clip_ratio=1.0, n_out=None):
     _need_cuda(x)
     assert x.dtype == torch.float16
@@ -93,6 +123,7 @@ def act_quant_i8_dynamic(x, clip_ratio=1.0, n_out=None):
     return q, srow
 
 
+@_on_device
 def hadamard(x, had_k=1, hadk=None, n=None, scales=None, modality=None, want_codes=False,
              want_f16=True, split=False, fp32_had=False, want_row_scales=True):
     """mq_hadamard_quant_i8.  Returns dict(y=fp16 [M,n] | None, q=int8 [M,n] | None, s_row, x0)."""
@@ -115,6 +146,21 @@ def hadamard(x, had_k=1, hadk=None, n=None, scales=None, modality=None, want_cod
     return {"y": y, "q": q, "s_row": srow, "x0": x0}
 
 
+@_on_device
+def hadamard_transform(x, scale):
+    """mq_hadamard_transform_f16: y = fp16(fp32(x . H_n) * scale) along the last dim (the seam of
+    fast_hadamard_transform.hadamard_transform); any leading shape, result contiguous."""
+    _need_cuda(x)
+    assert x.dtype == torch.float16
+    x2 = _as_rows(x)
+    M, n = x2.shape
+    y = torch.empty((M, n), dtype=torch.float16, device=x.device)
+    check(lib().mq_hadamard_transform_f16(_ptr(x2), _ld(x2), _ptr(y), n, M, n, float(scale), _stream()),
+          "mq_hadamard_transform_f16")
+    return y.reshape(x.shape)
+
+
+@_on_device
 def observer_minmax(x, state, per_channel=False):
     """mq_observer_minmax: merge x's min/max into `state` (fp32 [2] or [2*C], zero-initialised)."""
     _need_cuda(x, state)
@@ -127,6 +173,7 @@ def observer_minmax(x, state, per_channel=False):
     return state
 
 
+@_on_device
 def observer_minmax_msq(x, modality, state_text, state_visual, seen):
     """mq_observer_minmax_msq: one pass, rows with modality == 0 -> state_text, others ->
     state_visual (fp32 [2] each), row counts added to `seen` (int32 [2])."""
@@ -142,6 +189,7 @@ def observer_minmax_msq(x, modality, state_text, state_visual, seen):
 _pct_ws = {}
 
 
+@_on_device
 def observer_percentile(x, alpha=0.99999):
     """mq_observer_percentile -> fp32 [2] = {quantile(1-alpha), quantile(alpha)}."""
     _need_cuda(x)
@@ -160,6 +208,7 @@ def observer_percentile(x, alpha=0.99999):
     return out
 
 
+@_on_device
 def weight_quant_rtn(W, bits=4, scales=None):
     """mq_weight_quant_rtn.  W: [N, K] fp16.  Returns (codes int8 [N,K], s_w fp32 [N])."""
     _need_cuda(W, scales)
@@ -176,6 +225,7 @@ def weight_quant_rtn(W, bits=4, scales=None):
     return codes, s_w
 
 
+@_on_device
 def pack_w4(codes, zero_col0=False):
     _need_cuda(codes)
     assert codes.dtype == torch.int8 and codes.dim() == 2
@@ -190,6 +240,7 @@ def pack_w4(codes, zero_col0=False):
     return w4
 
 
+@_on_device
 def repack_w4_from_ref(ref_packed, N, K):
     _need_cuda(ref_packed)
     assert ref_packed.dtype == torch.uint8 and ref_packed.shape == (N, K // 2)
@@ -200,6 +251,7 @@ def repack_w4_from_ref(ref_packed, N, K):
     return w4
 
 
+@_on_device
 def unpack_w4(w4, N, K):
     _need_cuda(w4)
     codes = torch.empty((N, K), dtype=torch.int8, device=w4.device)
@@ -207,6 +259,7 @@ def unpack_w4(w4, N, K):
     return codes
 
 
+@_on_device
 def w4a8_gemm(q, w4, s_a, s_w, N, bias=None, x0=None, w0=None, out=None, simt=False):
     """mq_w4a8_gemm.  q: int8 [M, K]; s_a: fp32 [M] (per row) or [1]; s_w fp32 [N]."""
     _need_cuda(q, w4, s_a, s_w, bias, x0, w0)

@@ -131,6 +131,21 @@ def main():
                 rec(f"hadamard_quant_k{K_}", f"{M}x{C}", sec, best, bytes_=3 * M * C + M)
             del x
 
+    if a.only and "hadsweep" in a.only.split(","):
+        # fused Hadamard + INT8 quantiser at M = 16384 for every online-rotation
+        # width of the model table; bytes = 2*n_in read + n written + M
+        M = 16384
+        for n, n_in in ((1024, 1024), (2048, 2048), (4096, 4096), (8192, 8192), (11008, 11008), (13824, 13696),
+                        (14336, 14336), (19968, 18944), (5120, 5120)):
+            x = (torch.randn(M, n_in, device="cuda") * 3).half()
+            mod = (torch.rand(M, device="cuda") < 0.4).to(torch.uint8)
+            hk_, K_ = hu.get_hadK(n)
+            hk = hu.hadK_device(K_, "cuda") if K_ > 1 else None
+            sec, best = timeit(lambda: ops.hadamard(x, had_k=K_, hadk=hk, n=n, scales=scales, modality=mod,
+                                                    want_codes=True, want_f16=False))
+            rec(f"hadamard_quant_k{K_}", f"{M}x{n_in}->{n}", sec, best, bytes_=(2 * n_in + n) * M + M)
+            del x
+
     if want("gemm"):
         shapes = [(4096, 4096), (4096, 11008), (11008, 4096)]
         for M in ([16, 4096] if a.quick else [16, 256, 1024, 4096, 16384]):
