@@ -130,6 +130,7 @@ __device__ __forceinline__ uint32_t q8_exact(float x, float s) {
 struct QScale {
   float s, inv_lo, inv_hi;
   __half2 lim_lo, lim_hi;
+  bool narrow;  // s has at most 11 significant bits (an fp16- or bf16-valued scale): see quant8
 };
 __device__ __forceinline__ QScale make_qscale(float s) {
   QScale q;
@@ -139,6 +140,7 @@ __device__ __forceinline__ QScale make_qscale(float s) {
   q.inv_hi = __fmul_rn(inv, 1.0f + 2.384185791015625e-07f);
   q.lim_hi = __float2half2_rn(fminf(__fmul_rn(127.0f, s), 65504.f));
   q.lim_lo = __float2half2_rn(fmaxf(__fmul_rn(-128.0f, s), -65504.f));
+  q.narrow = (__float_as_uint(s) & 0x1fffu) == 0u;
   return q;
 }
 
@@ -163,8 +165,9 @@ __device__ __forceinline__ uint4 pack8_f16(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
   return v;
 }
-// 8 halfs (one uint4) -> 8 int8 codes (one uint2); bit-exact w.r.t. quant_code_exact
-__device__ __forceinline__ uint2 quant8(const uint4& v, const QScale& q) {
+// 8 halfs (one uint4) -> 8 int8 codes (one uint2); bit-exact w.r.t. quant_code_exact for ANY
+// fp32 scale (dynamic per-token scales, percentile scales)
+__device__ __forceinline__ uint2 quant8_bracket(const uint4& v, const QScale& q) {
   const __half2* h = reinterpret_cast<const __half2*>(&v);
   uint32_t t[8];
   uint32_t diff = 0;
@@ -202,6 +205,60 @@ __device__ __forceinline__ uint2 quant8(const uint4& v, const QScale& q) {
   r.x = pack4_lowbytes(t[0], t[1], t[2], t[3]);
   r.y = pack4_lowbytes(t[4], t[5], t[6], t[7]);
   return r;
+}
+// ---- narrow scales: no comparison, no slow path ------------------------------------------------
+// MinmaxObserver scales are fp16 (bf16) VALUES: s = S * 2^b with an integer S < 2^11, like every
+// activation x = X * 2^a.  Then x / s - (k + 1/2) = (X 2^(a-b+1) - S (2k+1)) / (2 S) is either 0
+// (an exact tie) or at least 1/(2S) > 2^-12 away from zero, i.e. >= 2^-20 relative for |x/s| <=
+// 128 -- wider than the bracket (x*inv_lo, x*inv_hi), 2^-21.4 relative.  So the two ends of the
+// bracket round to different integers ONLY at exact ties, where they are k and k+1, and
+//   fl(t_lo + t_hi) = 2M + 2k + 1 -> rounded to a multiple of 2 (ulp of [2^24, 2^25)), ties to an
+//   even mantissa = 2 (M + even(k, k+1))
+// is round-half-to-even: bits = 0x4BC00000 + code whether the ends agree or not.  One packed add
+// replaces the per-element comparison, the branch and the division fallback.
+// packed constants of a narrow scale
+struct QNarrow {
+  uint64_t inv_lo2, inv_hi2;
+  __half2 lim_lo, lim_hi;
+};
+__device__ __forceinline__ QNarrow make_qnarrow(const QScale& q) {
+  QNarrow n;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(n.inv_lo2) : "f"(q.inv_lo));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(n.inv_hi2) : "f"(q.inv_hi));
+  n.lim_lo = q.lim_lo;
+  n.lim_hi = q.lim_hi;
+  return n;
+}
+// two fp16 values (one 32-bit word) -> two fp32 words whose LOW BYTES are the codes
+__device__ __forceinline__ void quant2_narrow(uint32_t w, const QNarrow& q, uint32_t& c0, uint32_t& c1) {
+  uint64_t magic2;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(magic2) : "f"(MQ_RND_MAGIC));
+  const float2 f = __half22float2(__hmin2(__hmax2(*reinterpret_cast<const __half2*>(&w), q.lim_lo), q.lim_hi));
+  uint64_t x, lo, hi, sum;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(f.x), "f"(f.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(lo) : "l"(x), "l"(q.inv_lo2), "l"(magic2));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(hi) : "l"(x), "l"(q.inv_hi2), "l"(magic2));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(sum) : "l"(lo), "l"(hi));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(c0), "=r"(c1) : "l"(sum));
+}
+// four fp16 values in two words (a = elements 0,1; b = elements 2,3) -> 4 codes, byte i = element i
+__device__ __forceinline__ uint32_t quant4_narrow(uint32_t a, uint32_t b, const QNarrow& q) {
+  uint32_t t0, t1, t2, t3;
+  quant2_narrow(a, q, t0, t1);
+  quant2_narrow(b, q, t2, t3);
+  return pack4_lowbytes(t0, t1, t2, t3);
+}
+__device__ __forceinline__ uint2 quant8_narrow(const uint4& v, const QNarrow& n) {
+  uint2 r;
+  r.x = quant4_narrow(v.x, v.y, n);
+  r.y = quant4_narrow(v.z, v.w, n);
+  return r;
+}
+// 8 halfs -> 8 codes: narrow scales take the branch-free path, any other scale the bracket with
+// its division fallback (kernels hoist the test out of their loops where it matters)
+__device__ __forceinline__ uint2 quant8(const uint4& v, const QScale& q) {
+  if (q.narrow) return quant8_narrow(v, make_qnarrow(q));
+  return quant8_bracket(v, q);
 }
 // same from 8 floats that already hold fp16 values (Hadamard epilogues)
 __device__ __forceinline__ uint2 quant8(const float (&f)[8], const QScale& q) {

@@ -74,42 +74,19 @@ __device__ __forceinline__ uint32_t bf2_bits(float lo, float hi) {
   return r;
 }
 
-// per-token quantiser constants in the packed form the fast path consumes
+// per-token quantiser constants (narrow-scale fast path of mq_common.cuh + the scale itself)
 struct QPack {
-  uint64_t inv_lo2, inv_hi2;
-  __half2 lim_lo, lim_hi;
+  QNarrow n;
   float s;
+  bool narrow;
 };
 __device__ __forceinline__ QPack make_qpack(float s) {
   const QScale q = make_qscale(s);
   QPack p;
-  p.inv_lo2 = f2_pack(q.inv_lo, q.inv_lo);
-  p.inv_hi2 = f2_pack(q.inv_hi, q.inv_hi);
-  p.lim_lo = q.lim_lo;
-  p.lim_hi = q.lim_hi;
+  p.n = make_qnarrow(q);
   p.s = s;
+  p.narrow = q.narrow;
   return p;
-}
-
-// two fp16 pairs (a = elements 0,1; b = elements 2,3 of a 4-byte group) -> 4 codes.  Same exact
-// bracketing quantiser as quant8 (mq_common.cuh); `und` collects the undecided flag.
-__device__ __forceinline__ uint32_t quant4(uint32_t a, uint32_t b, const QPack& q, uint32_t& und) {
-  const uint64_t magic2 = f2_pack(MQ_RND_MAGIC, MQ_RND_MAGIC);
-  uint32_t t[4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const uint32_t w = i ? b : a;
-    const float2 f = __half22float2(__hmin2(__hmax2(*reinterpret_cast<const __half2*>(&w), q.lim_lo), q.lim_hi));
-    const uint64_t x = f2_pack(f.x, f.y);
-    uint64_t lo, hi;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(lo) : "l"(x), "l"(q.inv_lo2), "l"(magic2));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(hi) : "l"(x), "l"(q.inv_hi2), "l"(magic2));
-    uint32_t h0, h1;
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(t[2 * i]), "=r"(t[2 * i + 1]) : "l"(lo));
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(h0), "=r"(h1) : "l"(hi));
-    und |= (t[2 * i] ^ h0) | (t[2 * i + 1] ^ h1);
-  }
-  return pack4_lowbytes(t[0], t[1], t[2], t[3]);
 }
 // slow path: redo the 4 codes of a group with the true division
 __device__ __noinline__ uint32_t quant4_exact(uint32_t a, uint32_t b, float s) {
@@ -131,6 +108,9 @@ struct Traits {
   static constexpr int CH = 1 << FB;
   static constexpr int BL = NB / CH;
   static constexpr int MIN_CTAS = BL >= 16 ? 3 : BL >= 8 ? 4 : 5;
+  // two token buffers per warp while 4 warps x MIN_CTAS x 2 x N halfs fit in shared memory: the
+  // next token loads while this one is computed (measured: 8 us of exposed load latency at n = 4096)
+  static constexpr int NBUF = (MIN_CTAS * 4 * 2 * N * 2 <= 200 * 1024) ? 2 : 1;
   static_assert(FOLD >= 4 + FB, "scale folding");
 };
 
@@ -138,15 +118,14 @@ struct Traits {
 template <int NB, int FB, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, Traits<NB, FB>::MIN_CTAS) fwht_mma_kernel(const HadArgs a) {
   using T = Traits<NB, FB>;
-  constexpr int N = T::N, CH = T::CH, BL = T::BL;
+  constexpr int N = T::N, CH = T::CH, BL = T::BL, NBUF = T::NBUF;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  // per warp: ONE token buffer of N halfs (more resident warps hide the load latency better than a
-  // second buffer would), then (after all warps' buffers) one mbarrier
-  uint8_t* wbuf = smem + (size_t)warp * (N * 2);
+  // per warp: NBUF token buffers of N halfs, then (after all warps' buffers) NBUF mbarriers
+  uint8_t* wbuf = smem + (size_t)warp * (NBUF * N * 2);
   const uint32_t buf0 = smem_u32(wbuf);
-  const uint32_t bar0 = smem_u32(smem + (size_t)WARPS * (N * 2)) + warp * 8;
+  const uint32_t bar0 = smem_u32(smem + (size_t)WARPS * (NBUF * N * 2)) + warp * 16;
 
   // ---- constant fragments ------------------------------------------------------------------------
   // A1[m][kk] = +-2^-(4+FB), sign = parity(m3 kk0 + m1 kk1 + m2 kk2 + m0 kk3)
@@ -180,9 +159,12 @@ __global__ void __launch_bounds__(WARPS * 32, Traits<NB, FB>::MIN_CTAS) fwht_mma
 
   // ---- buffer: zero the padding tail once, barrier -----------------------------------------------
   const uint32_t row_bytes = (uint32_t)a.n_in * 2u;
-  for (int c = a.n_in / 8 + lane; c < N / 8; c += 32) *reinterpret_cast<uint4*>(wbuf + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+  for (int b = 0; b < NBUF; ++b)
+    for (int c = a.n_in / 8 + lane; c < N / 8; c += 32)
+      *reinterpret_cast<uint4*>(wbuf + (size_t)b * N * 2 + c * 16) = make_uint4(0u, 0u, 0u, 0u);
   if (lane == 0) {
     mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -204,17 +186,24 @@ __global__ void __launch_bounds__(WARPS * 32, Traits<NB, FB>::MIN_CTAS) fwht_mma
     mbar_arrive_expect_tx(bar0, row_bytes);
     bulk_load(buf0, a.x + gw * a.ldx, row_bytes, bar0);
   }
-  const uint32_t src = buf0 + lane * 16;
   const int wofs = g + 8 * t;  // word (4 elements) inside a block, tile adds 32
-  uint32_t ph = 0;
-  for (int64_t m = gw; m < a.M; m += nw, ph ^= 1u) {
+  int it = 0;
+  for (int64_t m = gw; m < a.M; m += nw, ++it) {
+    const int cur = NBUF == 2 ? (it & 1) : 0;
+    const uint32_t ph = (uint32_t)(NBUF == 2 ? (it >> 1) : it) & 1u;
+    const uint32_t src = buf0 + cur * (N * 2) + lane * 16;
+    if (NBUF == 2 && m + nw < a.M && lane == 0) {
+      // the other buffer was last read one iteration ago (every lane passed the __syncwarp since)
+      mbar_arrive_expect_tx(bar0 + 8 * (cur ^ 1), row_bytes);
+      bulk_load(buf0 + (cur ^ 1) * (N * 2), a.x + (m + nw) * a.ldx, row_bytes, bar0 + 8 * (cur ^ 1));
+    }
     bool vis = false;
     if (want_q && a.modality != nullptr) vis = __ldg(a.modality + m) != 0;
     const QPack& qs = vis ? q_vis : q_text;
     if (lane == 0 && a.srow_out != nullptr && want_q) a.srow_out[m] = qs.s;
     int8_t* qrow = want_q ? a.q + m * (int64_t)a.n + 4 * wofs : nullptr;
     __half* yrow = want_y ? a.y + m * (int64_t)a.n + 4 * wofs : nullptr;
-    mbar_wait(bar0, ph);
+    mbar_wait(bar0 + 8 * cur, ph);
 
 #pragma unroll 1
     for (int ch = 0; ch < CH; ++ch) {  // output group: blocks ch * BL .. ch * BL + BL - 1
@@ -244,10 +233,10 @@ __global__ void __launch_bounds__(WARPS * 32, Traits<NB, FB>::MIN_CTAS) fwht_mma
           hmma_f16(d1, bh == 0 ? a1p : a1s[bh > 0 ? bh - 1 : 0], w.y, w.w);
         }
         if (ch == CH - 1 && bl == BL - 1) {
-          // last read of the buffer: refill it with this warp's next token while the rest of this
-          // one is computed
+          // last read of the buffer (single-buffer variant: refill it with this warp's next token
+          // while the rest of this one is computed)
           __syncwarp();
-          if (m + nw < a.M && lane == 0) {
+          if (NBUF == 1 && m + nw < a.M && lane == 0) {
             mbar_arrive_expect_tx(bar0, row_bytes);
             bulk_load(buf0, a.x + (m + nw) * a.ldx, row_bytes, bar0);
           }
@@ -304,9 +293,8 @@ __global__ void __launch_bounds__(WARPS * 32, Traits<NB, FB>::MIN_CTAS) fwht_mma
           const int col = b * 256 + 128 * tl;  // + group and word offsets, already in qrow / yrow
           if (want_y) *reinterpret_cast<uint2*>(yrow + col) = make_uint2(ha, hb);
           if (want_q) {
-            uint32_t und = 0;
-            uint32_t codes = quant4(ha, hb, qs, und);
-            if (und != 0) codes = quant4_exact(ha, hb, qs.s);
+            const uint32_t codes0 = qs.narrow ? quant4_narrow(ha, hb, qs.n) : quant4_exact(ha, hb, qs.s);  // (division: rare scales only)
+            uint32_t codes = codes0;
             if (b == 0 && tl == 0 && split && ch == 0 && lane == 0) {
               a.x0_out[m] = __ushort_as_half((unsigned short)(ha & 0xffffu));
               codes &= 0xffffff00u;
@@ -324,7 +312,7 @@ __global__ void __launch_bounds__(WARPS * 32, Traits<NB, FB>::MIN_CTAS) fwht_mma
 template <int NB, int FB, int MODE>
 static int launch_mode(const HadArgs& a, cudaStream_t st) {
   using T = Traits<NB, FB>;
-  const size_t smem = (size_t)WARPS * (T::N * 2) + WARPS * 8;
+  const size_t smem = (size_t)WARPS * (T::NBUF * T::N * 2) + WARPS * 16;
   MQ_CUDA(cudaFuncSetAttribute(fwht_mma_kernel<NB, FB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = (a.M + WARPS - 1) / WARPS;
   const int64_t cap = (int64_t)num_sms() * T::MIN_CTAS;
@@ -355,9 +343,9 @@ int launch_fwht_mma(const HadArgs& a, cudaStream_t st) {
     case 2048: return hadmma::launch<8, 1>(a, st);
     case 4096: {
       const char* fb = getenv("MQ_HAD_FB");  // experiment knob
-      if (fb && fb[0] == '0') return hadmma::launch<16, 0>(a, st);
+      if (fb && fb[0] == '2') return hadmma::launch<16, 2>(a, st);
       if (fb && fb[0] == '1') return hadmma::launch<16, 1>(a, st);
-      return hadmma::launch<16, 2>(a, st);
+      return hadmma::launch<16, 0>(a, st);
     }
     default: return hadmma::launch<32, 2>(a, st);
   }

@@ -257,6 +257,7 @@ hadk_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       qs.inv_hi = vis ? q_vis.inv_hi : q_text.inv_hi;
       qs.lim_lo = vis ? q_vis.lim_lo : q_text.lim_lo;
       qs.lim_hi = vis ? q_vis.lim_hi : q_text.lim_hi;
+      qs.narrow = vis ? q_vis.narrow : q_text.narrow;
       if (live && j == 0 && grp == 0 && a.srow_out != nullptr) a.srow_out[tok] = qs.s;
       mbar_wait(d2_full(d2), d2ph);
       tc_fence_after();

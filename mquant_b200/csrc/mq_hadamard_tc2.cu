@@ -279,6 +279,7 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       qs.inv_hi = vis ? q_vis.inv_hi : q_text.inv_hi;
       qs.lim_lo = vis ? q_vis.lim_lo : q_text.lim_lo;
       qs.lim_hi = vis ? q_vis.lim_hi : q_text.lim_hi;
+      qs.narrow = vis ? q_vis.narrow : q_text.narrow;
       if (live && (mrow & 63) == 0 && (NS == 1 || mrow == 0) && grp == 0 && a.srow_out != nullptr) a.srow_out[tok] = qs.s;
       mbar_wait(d2_full(d2), d2ph);
       if (warp == EPI_WARP0) stamp(prm, lu, 5);

@@ -23,6 +23,9 @@ act_quant_i8_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* __restric
                     const uint8_t* __restrict__ modality, const float* __restrict__ scales,
                     uint32_t total, FastDiv cpr, int n_in, int n_out, unsigned flags) {
   const QScale q_text = make_qscale(__ldg(scales)), q_vis = make_qscale(__ldg(scales + 1));
+  // fp16 / bf16-valued scales (every MinmaxObserver scale): branch-free quantiser
+  const bool narrow = q_text.narrow && q_vis.narrow;
+  const QNarrow n_text = make_qnarrow(q_text), n_vis = make_qnarrow(q_vis);
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += stride * kQuantUnroll) {
     uint4 va[kQuantUnroll], vb[kQuantUnroll];
@@ -51,12 +54,19 @@ act_quant_i8_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* __restric
       if (c >= total) break;
       const QScale& qs = vis[u] ? q_vis : q_text;
       uint4 out;
-      uint2 r = quant8(va[u], qs);  // zero-padded columns quantise to code 0
+      uint2 r, r2;  // zero-padded columns quantise to code 0
+      if (narrow) {
+        const QNarrow& qn = vis[u] ? n_vis : n_text;
+        r = quant8_narrow(va[u], qn);
+        r2 = quant8_narrow(vb[u], qn);
+      } else {
+        r = quant8_bracket(va[u], qs);
+        r2 = quant8_bracket(vb[u], qs);
+      }
       out.x = r.x;
       out.y = r.y;
-      r = quant8(vb[u], qs);
-      out.z = r.x;
-      out.w = r.y;
+      out.z = r2.x;
+      out.w = r2.y;
       if (col[u] == 0) {
         if (flags & MQ_FLAG_SPLIT) {
           x0_out[row[u]] = reinterpret_cast<const __half*>(&va[u])[0];
@@ -142,12 +152,12 @@ act_quant_i8_dynamic_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* _
     for (int col = lane << 4; col < n_out; col += 512) {
       uint4 out = make_uint4(0u, 0u, 0u, 0u);
       if (col + 8 <= n_in) {
-        uint2 r = quant8(__ldg(reinterpret_cast<const uint4*>(xr + col)), qs);
+        uint2 r = quant8_bracket(__ldg(reinterpret_cast<const uint4*>(xr + col)), qs);
         out.x = r.x;
         out.y = r.y;
       }
       if (col + 16 <= n_in) {
-        uint2 r = quant8(__ldg(reinterpret_cast<const uint4*>(xr + col + 8)), qs);
+        uint2 r = quant8_bracket(__ldg(reinterpret_cast<const uint4*>(xr + col + 8)), qs);
         out.z = r.x;
         out.w = r.y;
       }
