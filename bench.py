@@ -2,7 +2,7 @@
 """bench.py -- the driver's measurement contract for the MQuant quantized-linear hot path.
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
-    python bench.py --impl reference ...                      (CPU arm: the oracle port)
+    python bench.py --impl reference ...                      (CPU arm: the REAL reference wrappers)
 
 A "step" is one pass of the hot path over one batch of synthetic tokens: the 7 x 32 QuantLinear
 forwards of the Qwen-VL-Chat 9.6B LLM prefill (BASELINE.json configs[1]) -- per Linear one fused
@@ -13,9 +13,14 @@ value      tokens/s of the whole job, inputs resident in HBM, CUDA-event timed, 
 e2e        same through the public API with HOST buffers: per step the token batch's hidden states
            are copied from pinned host memory and the last-token outputs are read back
 roofline   dominant kernel (w4a8_gemm_v4_kernel): ops of all GEMM launches of a step / their summed
-           CUDA-event durations, against 2 x the measured bf16 tensor peak (INT8 runs at twice the
-           bf16 rate on B200; MEASURED_PEAKS.json has no INT8 entry)
-cpu_baseline  the oracle port of the reference's fake-quant layer on the host cores, bounded sample
+           CUDA-event durations.  MEASURED_PEAKS.json has no INT8 entry, so the denominator is
+           measured IN THIS RUN: cuBLASLt INT8 (torch._int_mm, 8192^3) back to back for ~1.5 s (the
+           sustained figure -- the GEMM is timed inside a long step); the library's burst figure
+           and the 4.5 POP/s nominal are reported beside it
+cpu_baseline  the reference's own ActQuantWrappers inside its own QWenBlock (oracle/_ref, staged by
+           oracle/build_ref.py) on the host cores, bounded sample; the oracle port if not staged
+calibration  BASELINE configs[2] in the same run: 256 synthetic samples through the InternVL2-8B
+           stack's observers, sharded over the ranks, ONE allreduce(MAX) merge; strong scaling
 Multi-GPU: token batches are data parallel, weights replicated, no collective (weak scaling).
 """
 from __future__ import annotations
@@ -53,70 +58,216 @@ def parse():
                     help="do not share the activation quantisation / GEMM launch between the Linears of a "
                          "block that read the same tensor (q/k/v, the two up projections)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-calibration", action="store_true", help="skip the configs[2] calibration measurement")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's fake-quant wrapper (oracle/mq_oracle.py:qlinear_fake)
+# CPU arm: the reference's own fake-quant wrappers on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_layer_sample(tokens=1024, reps=1):
-    """Time ONE decoder layer's 7 wrapped Linears (fake-quant fp16 semantics, the torch-CPU
-    operators the reference executes) on `tokens` tokens with all host threads.  Returns seconds
-    per layer (best of reps)."""
-    import torch
+class CpuLayer:
+    """One Qwen-VL decoder layer's 7 wrapped Linears on `tokens` tokens, ready to be timed.
 
-    from oracle import torch_port as TP
+    kind "reference": the REAL reference -- its QWenBlock (model/modeling_qwen_opt.py:390-420) with
+    its ActQuantWrappers (fake_quant/quant_utils.py:271-391), RTN W4, static INT8 minmax, online
+    Hadamard K = 172 on mlp.c_proj -- imported from oracle/_ref (staged by oracle/build_ref.py).
+    One block forward records every wrapper's input; a step then calls the 7 wrappers on those
+    inputs (the hot path of SURVEY.md section 8: attention / norms are not on it).
+    kind "port": oracle/torch_port.py, used only when oracle/_ref has not been staged."""
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    g = torch.Generator().manual_seed(0)
-    hidden, ffn = 4096, 11008
-    spec = [(hidden, hidden, True, False)] * 3 + [(hidden, hidden, False, False)] + \
-           [(hidden, ffn, False, False)] * 2 + [(ffn, hidden, False, True)]
-    layers = []
-    for k, n, bias, had in spec:
-        W = (torch.randn(n, k, generator=g) * 0.02)
-        s_w = W.abs().amax(1, keepdim=True).clamp(min=1e-5) / 7
-        Wfq = (s_w * (W / s_w).round().clamp(-8, 7)).half()
-        b = (torch.randn(n, generator=g) * 0.1).half() if bias else None
-        x = (torch.randn(tokens, k, generator=g) * 3).half()
-        hk, K = TP.hadK_tensor(k) if had else (None, None)
-        layers.append((x, Wfq, b, torch.tensor(0.12, dtype=torch.float16), hk, K))
-    best = float("inf")
-    with torch.no_grad():
-        for _ in range(reps):
+    def __init__(self, tokens=1024):
+        import torch
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.tokens = tokens
+        from oracle import build_ref
+
+        if build_ref.stage() is not None and build_ref.available():
+            from oracle import ref_block as RB
+
+            qu, hu, mq = build_ref.import_staged()
+            self.kind = "reference"
+            with torch.no_grad():
+                block, wrappers, _ = RB.build_reference_block(qu, hu, mq)
+                RB.calibrate(block, wrappers, mq, [RB.hidden_states(11, 256), RB.hidden_states(12, 256)])
+                grabbed = {}
+                hooks = [w.register_forward_hook(lambda m, i, o, n=n: grabbed.__setitem__(n, i[0].detach().clone()))
+                         for n, w in wrappers.items()]
+                RB.run_block(block, mq, RB.hidden_states(13, tokens))
+                for h in hooks:
+                    h.remove()
+            self.calls = [(wrappers[n], grabbed[n]) for n in wrappers]
+            self.sample = (f"the reference's QWenBlock: its 7 ActQuantWrappers (RTN W4, static INT8 minmax, online Hadamard "
+                           f"K=172) on {tokens} tokens")
+        else:
+            from oracle import torch_port as TP
+
+            self.kind = "port"
+            g = torch.Generator().manual_seed(0)
+            hidden, ffn = 4096, 11008
+            spec = [(hidden, hidden, True, False)] * 3 + [(hidden, hidden, False, False)] + \
+                   [(hidden, ffn, False, False)] * 2 + [(ffn, hidden, False, True)]
+            self.calls = []
+            for k, n, bias, had in spec:
+                W = (torch.randn(n, k, generator=g) * 0.02)
+                s_w = W.abs().amax(1, keepdim=True).clamp(min=1e-5) / 7
+                Wfq = (s_w * (W / s_w).round().clamp(-8, 7)).half()
+                b = (torch.randn(n, generator=g) * 0.1).half() if bias else None
+                x = (torch.randn(tokens, k, generator=g) * 3).half()
+                hk, K = TP.hadK_tensor(k) if had else (None, None)
+                args = (x, Wfq, b, torch.tensor(0.12, dtype=torch.float16), hk, K)
+                self.calls.append((lambda a=args: TP.qlinear_fake(*a), None))
+            self.sample = f"oracle port of 1 decoder layer (7 fake-quant Linears, online Hadamard K=172) on {tokens} tokens"
+
+    def step(self):
+        """Seconds for the 7 wrappers of one layer on self.tokens tokens."""
+        import torch
+
+        with torch.no_grad():
             t0 = time.perf_counter()
-            for x, Wfq, b, s, hk, K in layers:
-                TP.qlinear_fake(x, Wfq, b, s, hk, K)
-            best = min(best, time.perf_counter() - t0)
-    return best
+            for fn, x in self.calls:
+                if x is None:
+                    fn()
+                else:
+                    fn(x.clone())  # (the reference wrapper quantises its input in place on the split path)
+            return time.perf_counter() - t0
 
 
 def run_reference_arm(a):
-    """--impl reference: the reference's algorithm on the host cores (oracle port; the reference is
-    pure Python/PyTorch and /root/reference does not exist on the GPU box)."""
+    """--impl reference: the reference's own implementation of the path on the host cores.  A step is
+    a bounded sample -- ONE decoder layer (its 7 wrapped Linears) on 1024 tokens; ``ms_per_step`` is
+    the measured wall time of that step, ``value`` the whole-workload metric it implies (tokens/s
+    through all `layers` layers)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    tokens = 1024
     a.layers = a.layers or 32
-    for _ in range(min(a.warmup, 1)):
-        cpu_layer_sample(tokens)
-    ts = [cpu_layer_sample(tokens) for _ in range(max(1, min(a.steps, 3)))]
+    layer = CpuLayer(1024)
+    for _ in range(max(1, min(a.warmup, 2))):
+        layer.step()
+    ts = [layer.step() for _ in range(max(1, a.steps))]
     per_layer = sum(ts) / len(ts)
-    step_s = per_layer * a.layers  # a full 32-layer pass over `tokens` tokens
-    value = tokens / step_s
-    sample = f"1 decoder layer (7 fake-quant Linears, online Hadamard K=172) on {tokens} tokens, x{a.layers} layers"
+    value = layer.tokens / (per_layer * a.layers)
+    sample = f"{layer.sample}; value = tokens / (step time x {a.layers} layers)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
-        "steps": len(ts), "warmup": min(a.warmup, 1), "ms_per_step": step_s * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int8xint4->int32 (reference: fp16 fake-quant)",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "tokens_per_step": tokens, "layers": a.layers},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "steps": len(ts), "warmup": max(1, min(a.warmup, 2)), "ms_per_step": per_layer * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp16 fake-quant (reference arithmetic)",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "tokens_per_step": layer.tokens, "layers_per_step": 1,
+                   "layers_in_workload": a.layers, "step": "bounded sample: 1 of the workload's layers on 1024 tokens"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": layer.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def measure_int8_library_peak(torch, seconds=1.5):
+    """cuBLASLt INT8 GEMM (torch._int_mm, 8192^3) on this GPU, now: (burst TOP/s = best of 10,
+    sustained TOP/s = back to back for `seconds`).  The measured stand-in for the INT8 tensor peak
+    that MEASURED_PEAKS.json lacks."""
+    n = 8192
+    A = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda")
+    B = torch.randint(-128, 127, (n, n), dtype=torch.int8, device="cuda").t()
+    try:
+        for _ in range(3):
+            torch._int_mm(A, B)
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(A, B)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch._int_mm(A, B)
+        e1.record()
+        torch.cuda.synchronize()
+        sustained_ms = e0.elapsed_time(e1) / reps
+        ops_ = 2.0 * n ** 3
+        return ops_ / (best * 1e-3) / 1e12, ops_ / (sustained_ms * 1e-3) / 1e12
+    except Exception:  # noqa: BLE001  (no INT8 library GEMM in this torch build)
+        return None, None
+    finally:
+        del A, B
+
+
+def run_calibration(torch, dist, dev, rank, world, samples=256):
+    """BASELINE configs[2]: W4A8 static calibration of the InternVL2-8B LLM stack (minmax observers,
+    `samples` synthetic image+text samples of 256..2048 tokens, seed 0), samples sharded round-robin
+    over the ranks, statistics merged with ONE allreduce(MAX) (mquant_b200/dist.py), scales derived
+    from one device-to-host copy.  Timed region = this rank's observer passes + the merge (CUDA
+    events, max over ranks).  Strong scaling.  Verified bit-identical to sequential calibration."""
+    from mquant_b200 import dist as mqdist, quant_utils
+    from mquant_b200.prefill import QuantLinearStack
+
+    args = type("A", (), {"skip_names": []})()
+    g = torch.Generator().manual_seed(0)
+    lengths = torch.randint(256, 2049, (samples,), generator=g).tolist()
+    gains = (1.0 + torch.rand(samples, generator=g)).tolist()
+
+    def build():
+        return QuantLinearStack("internvl2-8b", device=dev, calibrate=False, skeleton=True)
+
+    stack = build()
+    pool = stack.make_inputs(2048, dev, seed=7, visual_span=256, seq_len=2048)
+
+    def sample(i):
+        S = lengths[i]
+        return {k: (v[:S] * gains[i]).to(torch.float16) if k != "mask" else v[:S] for k, v in pool.items()}
+
+    def run(stk, indices):
+        quant_utils.model_open_calibrate(stk, args)
+        for i in indices:
+            stk.observe_tokens(sample(i))
+
+    mine = mqdist.shard_indices(samples, rank, world)
+    run(stack, mine[:2])  # warm-up
+    mqdist.merge_calibration(stack)
+    stack = build()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    run(stack, mine)
+    e1.record()
+    n_merged = mqdist.merge_calibration(stack)
+    e2.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_merge = float(t[0]), float(t[1])
+    # bit-identical to sequential calibration (every rank recomputes the sequential answer)
+    ref = build()
+    run(ref, range(samples))
+    quant_utils.update_all_quantization_params(ref)
+    same = 1
+    la = quant_utils.find_qlayers(stack, layers=[quant_utils.ActQuantWrapper])
+    lb = quant_utils.find_qlayers(ref, layers=[quant_utils.ActQuantWrapper])
+    for name in la:
+        qa, qb = la[name].quantizer.quantizer, lb[name].quantizer.quantizer
+        for attr in ("scale", "scale_visual"):
+            x, y = getattr(qa, attr), getattr(qb, attr)
+            if (x is None) != (y is None) or (x is not None and not torch.equal(x.reshape(()), y.reshape(()))):
+                same = 0
+    flag = torch.tensor([same], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {"metric": "w4a8_static_calibration_samples_per_s", "value": samples / (ms_total * 1e-3),
+            "unit": "samples/s", "scaling": "strong", "n_gpus": world, "samples": samples, "tokens": sum(lengths),
+            "ms_total": ms_total, "ms_merge": ms_merge, "observers_merged": n_merged,
+            "wrappers": len(la), "collectives_in_merge": 1, "identical_to_sequential": bool(flag.item()),
+            "workload": "internvl2-8b LLM stack (5 wrappers x 32 layers, MSQ minmax observers, online Hadamard 28 x 512 "
+                        "with fp16 output on feed_forward.w2), samples of 256..2048 tokens (seed 0)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -274,27 +425,35 @@ def main():
     n_gemm = gemm_launches[0]
     gemm_ops = stack.gemm_ops_per_token() * a.tokens
     achieved = gemm_ops / (gemm_total_ms * 1e-3) / 1e12
+    # denominators: MEASURED_PEAKS.json has no INT8 entry -> measure the library INT8 GEMM here, now
+    int8_burst, int8_sustained = measure_int8_library_peak(torch)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        pk = json.load(open(peaks_path))
-        # No INT8 entry in MEASURED_PEAKS.json: INT8 issues at twice the bf16 rate.  The in-step GEMM
-        # EXCEEDS 2 x the *sustained* bf16 figure (that run was power limited at 1290 MHz; the INT8
-        # kernel holds ~1800 MHz), so the valid upper bound is 2 x the burst figure; the
-        # sustained-derived fraction is reported next to it.
-        peak = 2.0 * float(pk.get("bf16_tflops", 1590.0))
-        peak_sus = 2.0 * float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)))
-        peak_src = "2 x measured bf16_tflops burst (MEASURED_PEAKS.json; INT8 = 2x bf16 rate, no INT8 entry)"
+    pk = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    bf16_burst = float(pk.get("bf16_tflops", 1590.0))
+    bf16_sus = float(pk.get("bf16_tflops_sustained", 1400.0))
+    if int8_sustained:
+        # the GEMM is timed inside a long step (power-capped clocks): sustained library figure
+        peak, peak_src = int8_sustained, ("cuBLASLt INT8 torch._int_mm 8192^3, back to back ~1.5 s, measured in this run "
+                                          "(MEASURED_PEAKS.json has no INT8 entry)")
     else:
-        peak, peak_sus, peak_src = 2.0 * 1590.0, 2.0 * 1400.0, "2 x fallback bf16 (B200_PROFILING.md)"
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per
-    # launch, averaged over the step's shape mix); only meaningful for the default workload
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1e_gemm_traffic.json")
-    if os.path.exists(tpath) and a.tokens == 16384:
-        traffic = json.load(open(tpath)).get("avg_bytes_per_launch")
+        peak, peak_src = 2.0 * bf16_sus, "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (no INT8 library GEMM available)"
+    # DRAM traffic of the dominant kernel: ncu cannot run inside the bench, so this is the committed
+    # `ncu --set full` capture of the same four GEMM shapes at M = 16384 (bytes per launch, averaged
+    # over the step's shape mix), labelled as such
+    traffic, traffic_src = None, None
+    for name in ("r2_gemm_traffic.json", "r1e_gemm_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath) and a.tokens == 16384 and a.workload == "qwenvl-9.6b":
+            traffic = json.load(open(tpath)).get("avg_bytes_per_launch")
+            traffic_src = f"profiles/{name} (ncu --set full dram__bytes_read+write of the same shapes; not measured in this run)"
+            break
+    alg_bytes = stack.gemm_bytes_per_step(a.tokens) / max(n_gemm, 1)
     roofline = {"bound": "tensor", "kernel": "w4a8_gemm_v4_kernel", "achieved": achieved, "peak": peak,
-                "unit": "TOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "peak_2x_bf16_sustained": peak_sus, "frac_2x_bf16_sustained": achieved / peak_sus,
+                "unit": "TOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "peak_int8_library_burst": int8_burst, "frac_int8_library_burst": (achieved / int8_burst) if int8_burst else None,
+                "peak_2x_bf16_burst": 2.0 * bf16_burst, "frac_2x_bf16_burst": achieved / (2.0 * bf16_burst),
+                "peak_2x_bf16_sustained": 2.0 * bf16_sus, "frac_2x_bf16_sustained": achieved / (2.0 * bf16_sus),
                 "peak_nominal": 4500.0, "frac_nominal": achieved / 4500.0,
                 "avg_launch_ms": gemm_total_ms / max(n_gemm, 1), "launches_timed": n_gemm,
                 "share_of_step": gemm_total_ms / ms_step}
@@ -317,13 +476,18 @@ def main():
         "gpu_launches": stack.launches_per_step() * a.steps,
         "roofline": roofline,
     }
+    if not a.no_calibration:
+        del stack, inputs, e2e_inputs, one
+        torch.cuda.empty_cache()
+        line["calibration"] = run_calibration(torch, dist, dev, rank, world)
     if rank == 0 and world == 1 and not a.no_cpu_baseline and a.workload == "qwenvl-9.6b":
         cores = os.cpu_count() or 1
-        tok = 1024
-        per_layer = cpu_layer_sample(tok)
+        layer = CpuLayer(1024)
+        layer.step()
+        per_layer = min(layer.step() for _ in range(3))
         line["cpu_baseline"] = {
-            "value": tok / (per_layer * a.layers), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 decoder layer (7 fake-quant Linears, online Hadamard K=172) on {tok} tokens, x{a.layers} layers",
+            "value": layer.tokens / (per_layer * a.layers), "unit": UNIT, "cores": cores, "kind": layer.kind,
+            "sample": f"{layer.sample}, best of 3; value = tokens / (time x {a.layers} layers)",
         }
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -192,6 +192,17 @@ int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4, const floa
                     const void* w0, void* out, int64_t ldo, int64_t M, int64_t N, int64_t K,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Which kernel mq_w4a8_gemm_ws runs for a shape and workspace size: 1 = weight-streaming dp4a
+ * (decode), 2 = split-K tcgen05, 3 = 128 x 256 tcgen05, 4 = 256 x 256 tcgen05; 0 = invalid
+ * shape.  Pure function of its arguments and the SM count (diagnostics / tests). */
+int mq_w4a8_gemm_plan(int64_t M, int64_t N, int64_t K, size_t workspace_bytes);
+
+/* Test / tooling overrides of the dispatchers (process-wide; return the previous value):
+ *   mq_debug_force_gemm_kernel(3 | 4)  always run the 128 x 256 / 256 x 256 tcgen05 kernel, 0 = auto
+ *   mq_debug_force_hadamard_kernel(1)  CUDA-core Hadamard kernels only (cross-checks), 0 = auto */
+int mq_debug_force_gemm_kernel(int kernel);
+int mq_debug_force_hadamard_kernel(int kind);
+
 /* CUDA-core reference of the same contract (slow; cross-check only, never on the product
  * path). */
 int mq_w4a8_gemm_simt(const int8_t* qa, int64_t lda, const uint8_t* w4, const float* s_a,

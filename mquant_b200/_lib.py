@@ -42,6 +42,9 @@ SIGNATURES = {
     "mq_unpack_w4": (_i, [_p, _p, _i64, _i64, _i64, _p]),
     "mq_w4a8_gemm": (_i, [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
     "mq_w4a8_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "mq_w4a8_gemm_plan": (_i, [_i64, _i64, _i64, _sz]),
+    "mq_debug_force_gemm_kernel": (_i, [_i]),
+    "mq_debug_force_hadamard_kernel": (_i, [_i]),
     "mq_w4a8_gemm_ws": (_i, [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _sz, _p]),
     "mq_w4a8_gemm_simt": (_i, [_p, _i64, _p, _p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p]),
 }

@@ -2,7 +2,12 @@
 #include "mq_common.cuh"
 #include "mq_tc.cuh"
 
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace mq {
 
@@ -34,6 +39,31 @@ int num_sms() {
   return cached;
 }
 
+int ensure_dyn_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;  // (kernel, device) -> bytes granted
+  int dev = 0;
+  MQ_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  int& have = done[std::make_pair(kernel, dev)];
+  if (have >= bytes) return MQ_OK;
+  MQ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  have = bytes;
+  return MQ_OK;
+}
+
+static std::atomic<int> g_force_hadamard{0};
+int forced_hadamard_kernel() { return g_force_hadamard.load(std::memory_order_relaxed); }
+
+#ifdef MQ_PROBES
+namespace gemm {
+unsigned probe_mask() {
+  const char* e = getenv("MQ_GEMM_DEBUG");
+  return e ? (unsigned)atoi(e) : 0u;
+}
+}  // namespace gemm
+#endif
+
 namespace tc {
 EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -51,6 +81,10 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace mq
 
 extern "C" int mq_version(void) { return MQ_VERSION; }
+
+extern "C" int mq_debug_force_hadamard_kernel(int kind) {
+  return mq::g_force_hadamard.exchange(kind == 1 ? 1 : 0);
+}
 
 extern "C" const char* mq_last_error(void) { return mq::g_err; }
 

@@ -20,6 +20,10 @@ namespace mq {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int num_sms();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of per launch
+int ensure_dyn_smem(const void* kernel, int bytes);
+// test / tooling overrides (mq_debug_force_*): 0 = automatic dispatch
+int forced_hadamard_kernel();
 
 #define MQ_REQUIRE(cond, ...)       \
   do {                              \
@@ -33,6 +37,12 @@ int num_sms();
   do {                                                  \
     cudaError_t _e = (call);                            \
     if (_e != cudaSuccess) return mq::cuda_fail(_e, #call); \
+  } while (0)
+
+#define MQ_DYN_SMEM(kernel, bytes)                                             \
+  do {                                                                         \
+    const int _rc = mq::ensure_dyn_smem((const void*)(kernel), (int)(bytes));  \
+    if (_rc != MQ_OK) return _rc;                                              \
   } while (0)
 
 #define MQ_LAUNCH_CHECK(name)                                      \

@@ -34,8 +34,18 @@ struct Params {
   int64_t ldo;
   int M, N, K;
   int m_tiles, n_tiles, k_tiles;
-  unsigned dbg;  // MQ_GEMM_DEBUG bottleneck probes (results are garbage when non-zero)
+  unsigned dbg;  // bottleneck probes (MQ_PROBES builds only; results are garbage when non-zero)
 };
+
+// Bottleneck probes (tools/gemm_probe.py): compiled OUT of the shipped library.  A probe build
+// (python -m mquant_b200.build --probes) defines MQ_PROBES and reads the mask from MQ_GEMM_DEBUG.
+#ifdef MQ_PROBES
+#define MQ_PROBE(p, mask) (((p).dbg & (mask)) != 0u)
+unsigned probe_mask();
+#else
+#define MQ_PROBE(p, mask) false
+static inline unsigned probe_mask() { return 0u; }
+#endif
 
 __device__ __forceinline__ void unpack_store(uint32_t brow, int rsw, int j, const uint4& p) {
   // low nibbles -> k = 32j .. 32j+15 (16-byte chunk 2j), high nibbles -> chunk 2j+1; values x16
@@ -50,9 +60,8 @@ __device__ __forceinline__ void unpack_store(uint32_t brow, int rsw, int j, cons
 }
 
 
-// mq_gemm_w4a8_v2.cu: second-generation kernel; two_cta selects the cta_group::2 flavour
-// (256 x 256 tile per CTA pair)
-int launch_w4a8_gemm_v2(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st, bool two_cta);
+// mq_gemm_w4a8_v2.cu: 128 x 256 tile per CTA, double-buffered TMEM accumulator
+int launch_w4a8_gemm_v2(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st);
 // mq_gemm_w4a8_v4.cu: 256 x 256 tile per CTA, one converted weight k-block shared by two M halves
 // (tmap_out: fp16 output, 32 x 32 boxes, SWIZZLE_64B -- the epilogue stores through TMA)
 int launch_w4a8_gemm_v4(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out, const Params& p, cudaStream_t st);
@@ -61,8 +70,6 @@ int launch_w4a8_gemm_v4(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out, 
 int splitk_factor(int64_t M, int64_t N, int64_t K);
 size_t splitk_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int launch_w4a8_gemm_sk(const CUtensorMap& tmap_a, const Params& p, void* workspace, cudaStream_t st);
-// mq_gemm_w4a8_v3.cu: register-path weights (no staging ring), two alternating converter groups
-int launch_w4a8_gemm_v3(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st);
 
 }  // namespace gemm
 

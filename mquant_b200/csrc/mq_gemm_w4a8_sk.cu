@@ -334,8 +334,6 @@ int splitk_factor(int64_t M, int64_t N, int64_t K) {
   if (3 * tiles > 2 * num_sms() || k_tiles < 8) return 1;
   int ksplit = (int)(num_sms() / tiles);
   if (ksplit > k_tiles / 4) ksplit = k_tiles / 4;
-  const char* env = getenv("MQ_SK_SPLIT");  // experiment knob: cap the split factor
-  if (env && atoi(env) >= 1 && atoi(env) < ksplit) ksplit = atoi(env);
   // measured (tools/latency.py, hot code / cold weights): the fixed cost of the reduction (atomics,
   // fence, counter, final pass by one CTA) is ~8 us -- a 2- or 3-way split only pays for long K
   if (ksplit < 2 || (ksplit < 4 && k_tiles < 64)) return 1;
@@ -359,10 +357,9 @@ int launch_w4a8_gemm_sk(const CUtensorMap& tmap_a, const Params& p_in, void* wor
   sp.ksplit = (p.k_tiles + sp.kbs - 1) / sp.kbs;
   sp.ws_acc = reinterpret_cast<int*>(workspace);
   sp.ws_cnt = reinterpret_cast<unsigned*>(sp.ws_acc + (size_t)tiles * BM * BN);
-  const char* probe = getenv("MQ_SK_PROBE");
-  sp.no_atomics = probe ? atoi(probe) : 0;
+  sp.no_atomics = 0;
   const int64_t work = tiles * sp.ksplit;
-  MQ_CUDA(cudaFuncSetAttribute(w4a8_gemm_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
+  MQ_DYN_SMEM(w4a8_gemm_sk_kernel, SM_ALLOC);
   const int grid = (int)(work < num_sms() ? work : num_sms());
   w4a8_gemm_sk_kernel<<<grid, NUM_THREADS, SM_ALLOC, st>>>(tmap_a, p, sp);
   return MQ_OK;

@@ -136,7 +136,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int mb = t / p.n_tiles;
         for (int kb = 0; kb < p.k_tiles; ++kb) {
           mbar_wait(aempty_bar(stage), phase ^ 1u);
-          if (p.dbg & 2u) {
+          if (MQ_PROBE(p, 2u)) {
             mbar_arrive(afull_bar(stage));
           } else {
             mbar_arrive_expect_tx(afull_bar(stage), A_STAGE);
@@ -149,7 +149,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 3) {
     // ===================== packed-weight producer: one 16 KB bulk copy per k-block
-    if (lane == 0 && !(p.dbg & 1u)) {
+    if (lane == 0 && !MQ_PROBE(p, 1u)) {
       int ws = 0;
       uint32_t wphase = 0;
       for (int t = unit; t < total_tiles; t += num_units) {
@@ -179,7 +179,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint32_t tmem_d = tmem_base + (uint32_t)(h * BN);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          if (!(p.dbg & 8u)) umma_i8(tmem_d, adesc + 2u * k, bdesc + 2u * k, IDESC, (uint32_t)((kb | k) != 0));
+          if (!MQ_PROBE(p, 8u)) umma_i8(tmem_d, adesc + 2u * k, bdesc + 2u * k, IDESC, (uint32_t)((kb | k) != 0));
         }
       }
       __syncwarp();
@@ -190,7 +190,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     };
     for (int t = unit; t < total_tiles; t += num_units, tile_phase ^= 1u) {
       const int K = p.k_tiles;
-      const bool edges = K >= 4 && !(p.dbg & 128u);
+      const bool edges = K >= 4 && !MQ_PROBE(p, 128u);
       int kb = 0;
       while (kb < K) {
         if (edges && (kb == 0 || kb == K - 2)) {
@@ -239,8 +239,8 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int r0 = threadIdx.x - CONV_WARP0 * 32;
     const int my_tiles = (total_tiles - unit + num_units - 1) / num_units;
     const int total_it = my_tiles * p.k_tiles;
-    const bool do_w = !(p.dbg & 1u);
-    const bool do_sts = !(p.dbg & (1u | 16u));
+    const bool do_w = !MQ_PROBE(p, 1u);
+    const bool do_sts = !MQ_PROBE(p, 1u | 16u);
     int stage = 0, ws = 0;
     uint32_t phase = 0, wphase = 0;
     // software pipelined as in v2: staging reads of k-block it+1 are issued before the proxy fence
@@ -343,7 +343,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const uint64_t sa2p = f2_pack(sa, sa), x0v2p = f2_pack(x0v, x0v);
         auto process = [&](const uint32_t (&v)[32], int cc) {
           const int colb = col0 + cc * 32;
-          if (p.dbg & 32u) return;  // probe: TMEM drain only
+          if (MQ_PROBE(p, 32u)) return;  // probe: TMEM drain only
           // the warp's staging tile (32 rows x 64 B, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk g of
           // row r sits at g ^ ((r >> 1) & 3)) is free once the previous TMA store has read it
           const uint32_t stg = stg0 + sbuf;
@@ -393,11 +393,11 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // volatile keeps it ordered with the fence and the TMA store below)
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w));
           }
-          if (!(p.dbg & 64u)) fence_async_smem();
+          if (!MQ_PROBE(p, 64u)) fence_async_smem();
           __syncwarp();
           // one TMA store per 32 x 32 block: whole 64-byte row segments, rows >= M and columns >= N
           // clipped by the tensor map
-          if (lane == 0 && !(p.dbg & 4u)) {
+          if (lane == 0 && !MQ_PROBE(p, 4u)) {
             tma_store_2d(&tmap_out, stg, nb * BN + colb, m_warp0);
             bulk_commit_group();
           }
@@ -432,7 +432,7 @@ static int launch_variant(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out
   using namespace v4;
   auto* kern = w4a8_gemm_v4_kernel<HAS_R1, HAS_BIAS>;
   constexpr int SM_ALLOC = Lay<HAS_R1, HAS_BIAS>::SM_ALLOC;
-  MQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_ALLOC));
+  MQ_DYN_SMEM(kern, SM_ALLOC);
   kern<<<grid, NUM_THREADS, SM_ALLOC, st>>>(tmap_a, tmap_out, p);
   return MQ_OK;
 }

@@ -141,7 +141,7 @@ w4a8_gemv_kernel(const Params p) {
 
 template <int M>
 static int launch(const Params& p, dim3 grid, size_t smem, cudaStream_t st) {
-  MQ_CUDA(cudaFuncSetAttribute(w4a8_gemv_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MQ_DYN_SMEM(w4a8_gemv_kernel<M>, smem);
   w4a8_gemv_kernel<M><<<grid, THREADS, smem, st>>>(p);
   return MQ_OK;
 }

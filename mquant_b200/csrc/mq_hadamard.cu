@@ -313,7 +313,7 @@ template <int LOG_N>
 static int launch_cta(const HadArgs& a, cudaStream_t st) {
   constexpr int N = 1 << LOG_N;
   const size_t smem = (size_t)(N + N / 8) * sizeof(float);
-  MQ_CUDA(cudaFuncSetAttribute(fwht_cta_kernel<LOG_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MQ_DYN_SMEM(fwht_cta_kernel<LOG_N>, smem);
   int64_t blocks = a.M;
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
@@ -325,7 +325,7 @@ template <int LOG_P>
 static int launch_hadk(const HadArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)a.n * ((a.flags & MQ_FLAG_FP32_HAD) ? 4 : 2);
   MQ_REQUIRE(smem <= 200 * 1024, "mq_hadamard_quant_i8: n=%d too large for the had_k>1 kernel", a.n);
-  MQ_CUDA(cudaFuncSetAttribute(hadk_simt_kernel<LOG_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MQ_DYN_SMEM(hadk_simt_kernel<LOG_P>, smem);
   int64_t blocks = a.M;
   const int64_t cap = (int64_t)num_sms() * 4;
   if (blocks > cap) blocks = cap;

@@ -23,9 +23,6 @@ struct HadArgs {
 };
 
 
-// mq_hadamard_tc.cu: both Kronecker factors on tcgen05 (first generation, MQ_HAD_KERNEL=tc1)
-bool hadk_tc_supported(const HadArgs& a);
-int launch_hadk_tc(const HadArgs& a, cudaStream_t st);
 // mq_hadamard_tc2.cu: power-of-two factor in registers, hadK factor on tcgen05 (default)
 bool hadk_tc2_supported(const HadArgs& a);
 int launch_hadk_tc2(const HadArgs& a, cudaStream_t st);

@@ -29,8 +29,6 @@
 // Tokens reach shared memory by cp.async.bulk (one per-warp double buffer, no CTA-wide barriers);
 // the zero padding from n_in to n is a tail of the buffer that the copies never touch.
 // HBM traffic per token: 2*n_in read + n written (codes) [+ 2*n if y_f16 is requested].
-#include <cstdlib>
-
 #include "mq_common.cuh"
 #include "mq_hadamard_args.cuh"
 #include "mq_tc.cuh"
@@ -313,7 +311,7 @@ template <int NB, int FB, int MODE>
 static int launch_mode(const HadArgs& a, cudaStream_t st) {
   using T = Traits<NB, FB>;
   const size_t smem = (size_t)WARPS * (T::NBUF * T::N * 2) + WARPS * 16;
-  MQ_CUDA(cudaFuncSetAttribute(fwht_mma_kernel<NB, FB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MQ_DYN_SMEM((fwht_mma_kernel<NB, FB, MODE>), smem);
   int64_t blocks = (a.M + WARPS - 1) / WARPS;
   const int64_t cap = (int64_t)num_sms() * T::MIN_CTAS;
   if (blocks > cap) blocks = cap;
@@ -332,21 +330,14 @@ bool fwht_mma_supported(const HadArgs& a) {
   if (a.had_k != 1) return false;
   if (a.n != 1024 && a.n != 2048 && a.n != 4096 && a.n != 8192) return false;
   if (a.n_in % 8 != 0 || a.ldx % 8 != 0) return false;
-  const char* off = getenv("MQ_HAD_SIMT");
-  if (off && atoi(off)) return false;
-  return true;
+  return forced_hadamard_kernel() != 1;
 }
 
 int launch_fwht_mma(const HadArgs& a, cudaStream_t st) {
   switch (a.n) {
     case 1024: return hadmma::launch<4, 0>(a, st);
     case 2048: return hadmma::launch<8, 1>(a, st);
-    case 4096: {
-      const char* fb = getenv("MQ_HAD_FB");  // experiment knob
-      if (fb && fb[0] == '2') return hadmma::launch<16, 2>(a, st);
-      if (fb && fb[0] == '1') return hadmma::launch<16, 1>(a, st);
-      return hadmma::launch<16, 0>(a, st);
-    }
+    case 4096: return hadmma::launch<16, 0>(a, st);  // (folding block bits into stage 1 does not pay here)
     default: return hadmma::launch<32, 2>(a, st);
   }
 }

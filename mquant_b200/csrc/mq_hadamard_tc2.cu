@@ -61,8 +61,13 @@ struct Cfg {
 struct Params {
   HadArgs a;
   Cfg c;
-  unsigned dbg;
+  unsigned dbg;  // bottleneck probes (MQ_PROBES builds only)
 };
+#ifdef MQ_PROBES
+#define MQ_HPROBE(prm, mask) (((prm).dbg & (mask)) != 0u)
+#else
+#define MQ_HPROBE(prm, mask) false
+#endif
 
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
@@ -86,7 +91,7 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
 // MQ_HAD_DEBUG bit 256: CTA 0 writes clock64() stamps into the (garbage anyway) code buffer,
 // 8 slots per unit, tools/had_probe.py --timeline prints them
 __device__ __forceinline__ void stamp(const Params& prm, int lu, int slot) {
-  if ((prm.dbg & 256u) && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && lu < 64)
+  if (MQ_HPROBE(prm, 256u) && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && lu < 64)
     reinterpret_cast<long long*>(prm.a.q)[lu * 8 + slot] = clock64();
 }
 
@@ -182,7 +187,7 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
         const int cnt = min(32, c.cpu - c0);
         for (int i = 0; i < cnt; ++i) {
           if (lane == i) {
-            if (prm.dbg & 32u) {  // probe: no loads
+            if (MQ_HPROBE(prm, 32u)) {  // probe: no loads
               mbar_arrive(x_full(xs));
             } else {
               mbar_arrive_expect_tx(x_full(xs), X_STAGE);
@@ -226,7 +231,7 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
           const uint32_t tm = tmem_base + (uint32_t)(d2 * D2_STRIDE + mt * c.acc_cols);
           const uint32_t tbase = sT + tb * c.t_buf + (uint32_t)(2 * mt) * lbo;
           for (int k = 0; k < c.Kpad / 16; ++k) {
-            if (prm.dbg & 8u) break;  // probe: no MMA
+            if (MQ_HPROBE(prm, 8u)) break;  // probe: no MMA
             const uint32_t boff = (uint32_t)(k / 4) * (uint32_t)(c.Kpad * 128) + (uint32_t)(k % 4) * 32u;
             umma_f16(tm, make_sw128_desc(tbase + (uint32_t)k * 2048u, lbo, 1024),
                      make_sw128_desc(sB2 + boff, 0, 1024), idesc, (uint32_t)(k != 0));
@@ -295,7 +300,7 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
         // independent quantiser streams give the scheduler the ILP that two epilogue warps per
         // SM sub-partition cannot (the epilogue is latency bound, not issue bound).
         auto process2 = [&](const uint32_t (&v0)[16], int ch0, const uint32_t (&v1)[16], bool two) {
-          if (prm.dbg & 2u) return;  // probe: TMEM loads only
+          if (MQ_HPROBE(prm, 2u)) return;  // probe: TMEM loads only
           uint32_t w[8];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -335,7 +340,7 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
         };
         uint32_t va[16], vb[16];
         int ch = grp;
-        if (prm.dbg & 64u) ch = chunks;  // probe: barrier handshake only
+        if (MQ_HPROBE(prm, 64u)) ch = chunks;  // probe: barrier handshake only
         for (; ch < chunks; ch += 4) {
           const bool two = ch + 2 < chunks;
           tmem_ld16_nowait(taddr + ch * 16, va);
@@ -367,7 +372,7 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
 #pragma unroll
       for (int cc = 0; cc < 8; ++cc) {
         uint4 rawv = make_uint4(0u, 0u, 0u, 0u);
-        if (!(prm.dbg & 128u))
+        if (!MQ_HPROBE(prm, 128u))
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(rawv.x), "=r"(rawv.y), "=r"(rawv.z), "=r"(rawv.w)
                      : "r"(xrow + ((uint32_t)(cc ^ (lane & 7)) << 4)));
@@ -380,7 +385,7 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(x_empty(xs));  // every lane's loads have been consumed above
-      if (!(prm.dbg & 16u)) {
+      if (!MQ_HPROBE(prm, 16u)) {
         // stage "xor 1" inside the packed pairs: (a, b) -> (a + b, a - b)
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -424,10 +429,10 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
           h[e] = *reinterpret_cast<const uint32_t*>(&hh);
         }
         const uint32_t dst = trow + ((uint32_t)(cc ^ (k & 7)) << 4);
-        if (!(prm.dbg & 4u))
+        if (!MQ_HPROBE(prm, 4u))
           asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
       }
-      if (!(prm.dbg & 128u)) fence_async_smem();
+      if (!MQ_HPROBE(prm, 128u)) fence_async_smem();
       __syncwarp();  // one arrival per chunk
       if (lane == 0) mbar_arrive(t_full(tb));
       if (ci == 0) stamp(prm, lu, 1);
@@ -469,15 +474,17 @@ static int launch(const HadArgs& a, cudaStream_t st) {
   if (b2r + NUM_XF_WARPS * X_STAGE + c.tb * c.t_buf > budget) return MQ_ERR_UNSUPPORTED;
   c.xs = (budget - b2r - c.tb * c.t_buf) / X_STAGE;
   if (c.xs > MAX_XSTAGES) c.xs = MAX_XSTAGES;
-  const char* xs_env = getenv("MQ_HAD_XSTAGES");  // experiment knob
-  if (xs_env && atoi(xs_env) >= 2 && atoi(xs_env) < c.xs) c.xs = atoi(xs_env);
   c.b2_off = 0;
   c.x_off = b2r;
   c.t_off = c.x_off + c.xs * X_STAGE;
   c.bar_off = c.t_off + c.tb * c.t_buf;
   c.total = c.bar_off + 8 * (2 * MAX_XSTAGES + 8) + 16;
+#ifdef MQ_PROBES
   const char* dbg_env = getenv("MQ_HAD_DEBUG");
   prm.dbg = dbg_env ? (unsigned)atoi(dbg_env) : 0u;
+#else
+  prm.dbg = 0u;
+#endif
 
   EncodeTiledFn encode = get_encode_fn();
   if (encode == nullptr) {
@@ -508,7 +515,7 @@ static int launch(const HadArgs& a, cudaStream_t st) {
     return MQ_ERR_CUDA;
   }
   const int smem = c.total + 1024;
-  MQ_CUDA(cudaFuncSetAttribute(hadk_tc2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  MQ_DYN_SMEM(hadk_tc2_kernel<NS>, smem);
   const int64_t units = (a.M + TPU - 1) / TPU;
   const int grid = (int)(units < num_sms() ? units : num_sms());
   hadk_tc2_kernel<NS><<<grid, NUM_THREADS, smem, st>>>(tmap, prm);
@@ -527,9 +534,7 @@ bool hadk_tc2_supported(const HadArgs& a) {
   const int Kpad = (a.had_k + 15) / 16 * 16;
   const int mt = P / 64 < 2 ? 1 : P / 128;
   if (mt * ((Kpad + 31) / 32 * 32) > hadtc2::D2_STRIDE) return false;  // accumulators of a unit: 256 TMEM columns
-  const char* off = getenv("MQ_HAD_SIMT");
-  if (off && atoi(off)) return false;
-  return true;
+  return forced_hadamard_kernel() != 1;
 }
 
 int launch_hadk_tc2(const HadArgs& a, cudaStream_t st) {

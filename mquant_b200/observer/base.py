@@ -2,6 +2,29 @@
 import torch
 
 
+def layerwise_rows(v, pad_ok):
+    """A 2-D [rows, C] fp16-kernel-friendly view of ``v`` for LAYER-WISE statistics, which do not
+    depend on the layout: activations [..., C] with C % 8 == 0 pass through; anything else (the
+    patch-embedding convolutions see [B, 3, H, W] / [N, 3, 2, 14, 14] inputs, reference
+    base.py:15-28 permutes them to channels-last with C = 3) is flattened and re-cut into rows of a
+    power-of-two width.  ``pad_ok``: a tail that does not fill a row may be zero padded (exact for
+    min/max, which fold 0 in anyway; not for quantiles)."""
+    C = v.shape[-1]
+    if v.dim() >= 2 and C % 8 == 0 and v.stride(-1) == 1:
+        return v.reshape(-1, C)
+    flat = v.reshape(-1)
+    n = flat.numel()
+    if n % 8 != 0:
+        if not pad_ok:
+            raise NotImplementedError(f"layer-wise observer: {n} elements is not a multiple of 8")
+        flat = torch.nn.functional.pad(flat, (0, 8 - n % 8))
+        n = flat.numel()
+    width = 8
+    while width < 4096 and n % (width * 2) == 0:
+        width *= 2
+    return flat.reshape(-1, width)
+
+
 class BaseObserver:
     def __init__(self, module_type, bit_type, calibration_mode):
         self.module_type = module_type

@@ -8,7 +8,7 @@ bit-identical to the reference's sequential update.
 import torch
 
 from .. import ops
-from .base import BaseObserver
+from .base import BaseObserver, layerwise_rows
 
 
 class MinmaxObserver(BaseObserver):
@@ -63,9 +63,14 @@ class MinmaxObserver(BaseObserver):
         if self.module_type != "activation":
             raise NotImplementedError("mquant_b200 observes activations only")
         v = v.detach()
-        if v.dim() == 4:
+        if not self._per_channel():
+            v = layerwise_rows(v, pad_ok=True)  # conv inputs: the scalar min/max ignore the layout
+        elif v.dim() == 4:
             v = v.permute(0, 2, 3, 1)
         C = v.shape[-1]
+        if self._per_channel() and C % 8 != 0:
+            raise NotImplementedError(f"channel-wise MinmaxObserver: {C} channels (needs a multiple of 8); "
+                                      "the drivers calibrate convolutions layer-wise")
         if self.state is None:
             n = 2 * C if self._per_channel() else 2
             self.state = torch.zeros(n, dtype=torch.float32, device=v.device)

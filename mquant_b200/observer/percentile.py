@@ -8,7 +8,7 @@ cannot be sharded across ranks bit-exactly (replicas only).
 import torch
 
 from .. import ops
-from .base import BaseObserver
+from .base import BaseObserver, layerwise_rows
 
 
 class PercentileObserver(BaseObserver):
@@ -21,9 +21,7 @@ class PercentileObserver(BaseObserver):
 
     def update(self, v):
         assert self.calibration_mode == "layer_wise"
-        v = v.detach()
-        if v.dim() == 4:
-            v = v.permute(0, 2, 3, 1)
+        v = layerwise_rows(v.detach(), pad_ok=False)  # the quantiles of the flattened tensor
         qs = ops.observer_percentile(v, self.percentile_alpha)
         cur_min, cur_max = qs[0], qs[1]
         if self.max_val is None:

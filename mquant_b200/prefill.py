@@ -95,9 +95,11 @@ def synthetic_tokens(n_tokens, width, device, seed=0, visual_span=256, seq_len=1
 
 class QuantLinearStack(torch.nn.Module):
     def __init__(self, model="qwenvl-9.6b", n_layers=None, device="cuda", seed=42, calib_tokens=2048,
-                 split=False, keep_fp16_weights=False, calibrate=True, fuse_siblings=False):
+                 split=False, keep_fp16_weights=False, calibrate=True, fuse_siblings=False, skeleton=False):
         """calibrate=False leaves the wrappers configured (static INT8, MSQ, minmax observers) but
         neither calibrated nor frozen -- the starting point of a (sharded) calibration run.
+        skeleton=True (with calibrate=False) builds the wrappers around 8-channel Linears: the
+        calibration hot path (rotation + observers) never touches the weights.
         fuse_siblings=True lets the Linears of a block that read the same tensor (q/k/v, the two
         up projections) share one activation quantisation and one GEMM launch (bit-identical)."""
         super().__init__()
@@ -109,7 +111,8 @@ class QuantLinearStack(torch.nn.Module):
         self.layers = torch.nn.ModuleList()
         torch.manual_seed(seed)
         args = _Args()
-        calib = {
+        assert not (skeleton and calibrate), "a skeleton stack has no weights to freeze"
+        calib = {} if not calibrate else {
             "h": synthetic_tokens(calib_tokens, hidden, device, 1)[0],
             "a": synthetic_tokens(calib_tokens, hidden, device, 2)[0],
             "h2": synthetic_tokens(calib_tokens, hidden, device, 3)[0],
@@ -120,6 +123,16 @@ class QuantLinearStack(torch.nn.Module):
             block = torch.nn.ModuleDict()
             for name, k_in, n_out, bias, had, kind in self.spec:
                 k_pad = hadamard_utils.auto_pad_size(k_in) if had else k_in
+                if skeleton:
+                    w = quant_utils.ActQuantWrapper(torch.nn.Linear(k_pad, 8, bias=False).half().to(device))
+                    if had:
+                        w.online_full_had = True
+                        w.had_K, w.K = hadamard_utils.get_hadK(k_pad)
+                        if k_pad != k_in:
+                            w.pad_to = k_pad
+                    w.quantizer.configure(bits=8, sym=True, static=True, observer_type="minmax", msq=True)
+                    block[name.replace(".", "_")] = w
+                    continue
                 lin = torch.nn.Linear(k_pad, n_out, bias=bias).half().to(device)
                 if k_pad != k_in:
                     lin.weight.data[:, k_in:] = 0  # the padded input columns are zero anyway
@@ -201,6 +214,14 @@ class QuantLinearStack(torch.nn.Module):
 
     def gemm_ops_per_token(self):
         return sum(2 * k * n for _, k, n, _, _, _ in self.spec) * self.n_layers
+
+    def gemm_bytes_per_step(self, n_tokens):
+        """Algorithmic bytes of the step's GEMM launches: N*K/2 + M*K + 2*M*N + 4*N."""
+        tot = 0
+        for _, k, n, _, had, _ in self.spec:
+            kp = hadamard_utils.auto_pad_size(k) if had else k
+            tot += n * kp // 2 + n_tokens * kp + 2 * n_tokens * n + 4 * n
+        return tot * self.n_layers
 
     def launches_per_step(self):
         # per Linear (or per fused sibling group): one activation kernel (quant or fused

@@ -23,6 +23,7 @@ There is no CPU execution path: forward on CPU tensors raises.
 from __future__ import annotations
 
 import math
+import warnings
 from collections import OrderedDict
 
 import torch
@@ -295,13 +296,15 @@ class ActQuantWrapper(torch.nn.Module):
 
     # -- real-integer path -----------------------------------------------------------------------
     @torch.no_grad()
-    def freeze(self, w_scale=None, w_bits=4):
+    def freeze(self, w_scale=None, w_bits=4, check=False):
         """Pack the current (fake-quantised, fp16) weight into INT4 for the W4A8 GEMM.
 
         w_scale: the per-output-channel scale the weight was quantised with
         (``WeightQuantizer.scale``, shape [N,1]); codes = round(W / scale) are then recovered
         exactly (SURVEY.md 8(c) self-check).  If omitted the weight is re-quantised RTN
         (quant_utils.py:446-466) -- identical codes when the weight already sits on a 4-bit grid.
+        check=True verifies that the packed integers reproduce the current weight exactly and raises
+        otherwise (model_freeze turns it on whenever weight quantizers were supplied).
         """
         if not isinstance(self.module, torch.nn.Linear):
             raise NotImplementedError("freeze(): only Linear layers have an integer path")
@@ -326,8 +329,30 @@ class ActQuantWrapper(torch.nn.Module):
             codes, s_w = ops.weight_quant_rtn(body, w_bits, w_scale)
             w0 = W[:, 0].contiguous()
         else:
+            body = W
             codes, s_w = ops.weight_quant_rtn(W, w_bits, w_scale)
             w0 = None
+        if check:
+            # the integer weights must BE the weights that were evaluated: a fake-quantised weight
+            # sits on its grid, so codes * scale reproduces it (to fp16 rounding).  A GPTQ / clipped
+            # weight re-quantised without its scale (max|W|/7 instead) does not.
+            orig = (torch.cat([self.L1.weight.data, self.L2.weight.data], 1) if self.split
+                    else self.module.weight.data)
+            # (L1 / L2 turn fp32 on their first reference-path call, quant_utils.py:374-375: compare
+            # what the fp16 weights were)
+            cmp_dtype = torch.float16 if orig.dtype == torch.float32 else orig.dtype
+            back = (codes.float() * s_w[:, None]).to(cmp_dtype)  # the reference's own expression (:52)
+            ref_w = orig.to(cmp_dtype).clone()
+            if self.split:
+                ref_w[:, 0] = 0
+            bad = (back != ref_w).any(dim=1)
+            if bool(bad.any()):
+                n_bad = int(bad.sum())
+                raise RuntimeError(
+                    f"freeze(): {n_bad} of {N} output channels are not reproduced by round(W/scale)*scale"
+                    + (" with the supplied scale" if w_scale is not None else
+                       " with the RTN scale max|W|/7 -- pass the WeightQuantizer scale the weight was "
+                       "quantised with (GPTQ / clip search), or check=False to re-quantise RTN"))
         Kp = _round_up(max(K, self.pad_to or 0), 128)
         if Kp != K:
             codes = torch.nn.functional.pad(codes, (0, Kp - K))
@@ -348,6 +373,8 @@ class ActQuantWrapper(torch.nn.Module):
         M = x2.shape[0]
         scales = qz.device_scales(x.device)
         modality = self.quantizer._modality(x) if qz.scale_visual is not None else None
+        if self.online_partial_had and not self.online_full_had:
+            x2 = self._partial_had(x2)
         if self.online_full_had:
             n = self.pad_to or x2.shape[-1]
             hk = hadamard_utils.hadK_device(self.K, x.device) if self.K > 1 else None
@@ -375,10 +402,29 @@ class ActQuantWrapper(torch.nn.Module):
             y = ops.hadamard(xh, had_k=self.K, hadk=hk, n=n, fp32_had=self.fp32_had)["y"]
             return y.reshape(*x.shape[:-1], n).to(x.dtype)
         if self.online_partial_had:
-            raise NotImplementedError("online_partial_had is never enabled by the reference drivers")
+            return self._partial_had(x)
         if self.pad_to and self.pad_to > x.shape[-1]:
             return torch.nn.functional.pad(x, (0, self.pad_to - x.shape[-1]))
         return x
+
+    def _partial_had(self, x):
+        """Per-head online Hadamard (reference quant_utils.py:343-365): the transform runs ACROSS
+        the n/had_dim heads for each of the had_dim positions, scale 1/sqrt(n/had_dim)."""
+        from .fht import hadamard_transform
+
+        x_dtype = x.dtype
+        if self.fp32_had:
+            x = x.float()
+        init_shape = x.shape
+        heads = init_shape[-1] // self.had_dim
+        if self.K == 1:
+            x = hadamard_transform(x.reshape(-1, heads, self.had_dim).transpose(1, 2).contiguous(),
+                                   scale=1 / math.sqrt(heads)).transpose(1, 2)
+        else:
+            x = (self.had_K.to(x.dtype) @ x.reshape(-1, heads, self.had_dim)) / math.sqrt(heads)
+        if self.fp32_had:
+            x = x.to(x_dtype)
+        return x.reshape(init_shape)
 
     def forward(self, x):
         x_dtype = x.dtype
@@ -387,7 +433,10 @@ class ActQuantWrapper(torch.nn.Module):
             if x.dtype == torch.float16:
                 return self._forward_real(x)
             if x.dtype == torch.bfloat16:
-                # the integer path computes in fp16 in / fp16 out (exact conversion of in-range bf16)
+                # the integer path computes in fp16 in / fp16 out (exact conversion of in-range bf16);
+                # a sibling group converts once and keys its cache on the ORIGINAL tensor
+                if self._group is not None:
+                    return self._group.forward(self, x).to(x_dtype)
                 return self._forward_real(x.clamp(-65504.0, 65504.0).to(torch.float16)).to(x_dtype)
 
         x = self._rotate(x)
@@ -703,10 +752,17 @@ class _SiblingGroup:
         idx = self.members.index(member)
         ver = self._version_of(x)
         hit = (ver is not None and self._x is x and self._ver == ver and idx not in self._served)
+        if not hit and (ver is None or (self._x is not None and idx in self._served)):
+            # sharing cannot be proven for this call (inference tensors carry no version counter;
+            # a member called twice in a row is not the q/k/v pattern): run the member's OWN GEMM
+            # instead of the concatenated one -- same result, a third (half) of the work
+            return self._forward_single(member, x)
         if not hit:
             w = self.first
             qz = w.quantizer.quantizer
             x2 = x.reshape(-1, x.shape[-1])
+            if x2.dtype == torch.bfloat16:
+                x2 = x2.clamp(-65504.0, 65504.0).to(torch.float16)
             scales = qz.device_scales(x.device)
             modality = w.quantizer._modality(x) if qz.scale_visual is not None else None
             q, srow, _ = ops.act_quant_i8(x2, scales, modality, n_out=self.Kp, split=False,
@@ -720,6 +776,24 @@ class _SiblingGroup:
         if len(self._served) == len(self.members):
             self.release()
         return y
+
+
+def _forward_single(self, member, x):
+    pk = member._packed
+    qz = member.quantizer.quantizer
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.dtype == torch.bfloat16:
+        x2 = x2.clamp(-65504.0, 65504.0).to(torch.float16)
+    scales = qz.device_scales(x.device)
+    modality = member.quantizer._modality(x) if qz.scale_visual is not None else None
+    q, srow, _ = ops.act_quant_i8(x2, scales, modality, n_out=pk["Kp"], split=False,
+                                  want_row_scales=modality is not None)
+    s_a = srow if modality is not None else scales[0:1]
+    out = ops.w4a8_gemm(q, pk["w4"], s_a, pk["s_w"], pk["N"], bias=pk["bias"])
+    return out.reshape(*x.shape[:-1], pk["N"])
+
+
+_SiblingGroup._forward_single = _forward_single
 
 
 def fuse_siblings(wrappers):
@@ -772,15 +846,143 @@ def model_freeze(model, args=None, weight_quantizers=None):
             continue
         ws = None
         for key, s in scales.items():
-            if key.endswith(name) or name.endswith(key):
+            if key == name or key.endswith("." + name) or name.endswith("." + key):
                 ws = s
                 break
-        layer.freeze(ws)
+        if weight_quantizers and ws is None:
+            warnings.warn(f"model_freeze: no weight-quantizer scale matches '{name}'; its weight is "
+                          "re-quantised RTN and verified against the fp16 weight", stacklevel=2)
+        layer.freeze(ws, check=bool(weight_quantizers))
         n += 1
     return n
 
 
-# ---- calibration protocol (reference calib_vqa_plus, :1079-1102, with synthetic batches) ----------
+@torch.no_grad()
+def update_all_quantization_params(model, args=None):
+    """Derive the scales of EVERY calibrated static wrapper of ``model`` at once: one device-to-host
+    copy of all layer-wise MinmaxObserver statistics, the reference's scale expression
+    (observer/minmax.py:30-46) evaluated on the host over all of them together, one copy back.
+    Same values as calling ``ActQuantizer.update_quantization_params()`` wrapper by wrapper (which
+    costs a device round trip per observer: 66 ms for 160 wrappers, profiles/r1e_multi_gpu_n2.log).
+    Other observer kinds fall back to their own update.  Returns the number of wrappers updated."""
+    from .observer.minmax import MinmaxObserver
+
+    skip = getattr(args, "skip_names", None) or []
+    fast, slow = [], []
+    for name, layer in find_qlayers(model, layers=[ActQuantWrapper]).items():
+        q = layer.quantizer
+        if any(p in name for p in skip) or not getattr(q, "static", False):
+            continue
+        obs = [q.observer] + ([q.observer_visual] if q.msq else [])
+        if all(type(o) is MinmaxObserver and not o._per_channel() for o in obs) and q.observer.symmetric:
+            if any(o.state is not None for o in obs):
+                fast.append(q)
+        elif any(_observed(o) for o in obs):
+            slow.append(q)
+    for q in slow:
+        q.update_quantization_params()
+    if not fast:
+        return len(slow)
+    dev = next(o.state.device for q in fast for o in ([q.observer] + ([q.observer_visual] if q.msq else []))
+               if o.state is not None)
+    rows = []
+    for q in fast:
+        zero2 = torch.zeros(2, dtype=torch.float32, device=dev)
+        t = q.observer.state if q.observer.state is not None else zero2
+        v = q.observer_visual.state if (q.msq and q.observer_visual.state is not None) else zero2
+        seen = getattr(q, "_seen", None)
+        if seen is None:  # (gather path / restored statistics: a state that exists has been seen)
+            seen = torch.tensor([float(q.observer.state is not None),
+                                 float(q.msq and q.observer_visual.state is not None)], device=dev)
+        rows.append(torch.cat([t.to(dev), v.to(dev), seen.to(dev, torch.float32)]))
+    host = torch.stack(rows).cpu()  # [n, 6] = {tmin, tmax, vmin, vmax, n_text, n_visual}: ONE copy
+    # the reference's expression, in the dtype of the statistics, for all observers at once
+    by_dtype = {}
+    for i, q in enumerate(fast):
+        dt = q.observer._dtype or (q.observer_visual._dtype if q.msq else None) or torch.float16
+        by_dtype.setdefault(dt, []).append(i)
+    bt = fast[0].observer.bit_type
+    scales = {}
+    for dt, idx in by_dtype.items():
+        h = host[idx]
+        eps = torch.finfo(torch.float32).eps
+        st = torch.max(torch.abs(h[:, 0].to(dt) / bt.lower_bound), torch.abs(h[:, 1].to(dt) / bt.upper_bound)).clamp_(eps)
+        sv = torch.max(torch.abs(h[:, 2].to(dt) / bt.lower_bound), torch.abs(h[:, 3].to(dt) / bt.upper_bound)).clamp_(eps)
+        for j, i in enumerate(idx):
+            scales[i] = (st[j], sv[j])
+    n = len(fast)
+    # text/visual scales of every wrapper as one device tensor; each quantizer keeps views of it
+    host_pairs, dts = [], []
+    for i, q in enumerate(fast):
+        has_t, has_v = bool(host[i, 4] > 0), bool(q.msq and host[i, 5] > 0)
+        st, sv = scales[i]
+        if not has_t and has_v:
+            st = sv  # only visual tokens were ever seen
+        host_pairs.append((st, sv if has_v else st, has_t or has_v, has_v and has_t))
+    for dt in by_dtype:
+        idx = by_dtype[dt]
+        pairs = torch.stack([torch.stack([host_pairs[i][0], host_pairs[i][1]]) for i in idx]).to(dev)  # [m, 2] in dt
+        f32 = pairs.float().contiguous()
+        for j, i in enumerate(idx):
+            q = fast[i]
+            _, _, any_seen, both = host_pairs[i]
+            if not any_seen:
+                continue
+            qz = q.quantizer
+            qz.scale = pairs[j, 0]
+            qz.zero_point = torch.zeros((), dtype=torch.int64, device=dev)
+            has_v = bool(q.msq and host[i, 5] > 0)
+            qz.scale_visual = pairs[j, 1] if has_v else None
+            qz._dev_scales = f32[j]
+    return n + len(slow)
+
+
+# ---- calibration entry points the drivers call (reference :1079-1129) ------------------------------
+
+def _calib_generate(model, args, dataset, calib_num, kwargs_attr, restore):
+    from tqdm import tqdm
+
+    lt = len(dataset.data)
+    step = math.ceil(lt / calib_num)
+    print("Calibrating...")
+    model_open_calibrate(model.model, args)
+    kw = getattr(model, kwargs_attr)
+    saved = kw.get("max_new_tokens") if restore else None
+    kw["max_new_tokens"] = 20
+    for i in tqdm(range(0, lt, step)):
+        if i + step >= lt:
+            print("last calibrate")
+            model_open_last_calibrate(model.model, args)
+            kw["max_new_tokens"] = 1
+        if hasattr(model, "use_custom_prompt") and model.use_custom_prompt(args.dataset_name):
+            struct = model.build_prompt(dataset.data.iloc[i], dataset=args.dataset_name)
+        else:
+            struct = dataset.build_prompt(dataset.data.iloc[i])
+        model.generate(message=struct, dataset=args.dataset_name)
+    if restore:
+        kw["max_new_tokens"] = saved
+    else:
+        setattr(model, kwargs_attr, {})
+    model_close_calibrate(model.model, args)
+    print("Calibrate End...")
+    model_quant(model.model, args)
+
+
+def calib_vqa_plus(model, args, dataset, calib_num):
+    """Reference quant_utils.py:1079-1102: ~calib_num evenly spaced samples of a VLMEvalKit dataset
+    through ``model.generate`` with the observers on (20 new tokens, 1 on the last sample, where the
+    scales are derived), then quantisation on.  ``model`` is the VLMEvalKit wrapper (``.model`` holds
+    the network, ``.kwargs`` the generation arguments)."""
+    _calib_generate(model, args, dataset, calib_num, "kwargs", restore=False)
+
+
+def calib_qwen2vl_plus(model, args, dataset, calib_num):
+    """Reference quant_utils.py:1105-1129: the same protocol for the Qwen2-VL wrapper, whose
+    generation arguments live in ``.generate_kwargs`` and are restored afterwards."""
+    _calib_generate(model, args, dataset, calib_num, "generate_kwargs", restore=True)
+
+
+# ---- the same protocol with caller-supplied batches (synthetic calibration, tests, bench) -----------
 
 @torch.no_grad()
 def calibrate_static(model, args, batches, forward=None):

@@ -250,6 +250,85 @@ def main():
     np.savez_compressed(os.path.join(OUT, "act_quant_bf16.npz"), calib=bits(torch.stack(calib)), x=bits(x),
                         scale=bits(q.quantizer.scale.reshape(1)), codes=q.quantizer.quant(x.float()).numpy(),
                         y=bits(y))
+    # ---------------------------------------------------------------- 9. wrapper forward, GPU-sized
+    # (appended after the cases above so that their random stream is unchanged)  The had344 / split
+    # cases of section 6 have n / had_k = 2, below what the CUDA kernels take (>= 64); the same
+    # wrapper configurations at K = 768 = 12 x 64 run on the GPU: online Hadamard K = 12, and the
+    # RMS split on top of it.
+    torch.manual_seed(9)
+    case = {}
+    for tag, K_in, N_out, bias, had, split in (("had768", 768, 64, False, True, False),
+                                               ("split768", 768, 64, True, True, True)):
+        lin = torch.nn.Linear(K_in, N_out, bias=bias).half()
+        hk, k = hu.get_hadK(K_in)
+        lin.weight.data = hu.matmul_hadU_cuda(lin.weight.data.float(), hk, k).half()
+        w = qu.ActQuantWrapper(lin)
+        w.online_full_had = True
+        w.had_K, w.K = hu.get_hadK(K_in)
+        if split:
+            w.split = True
+            w.split_weights()
+        t = w.L2 if split else w.module
+        wq = qu.WeightQuantizer()
+        wq.configure(4, perchannel=True, sym=True, mse=False)
+        wq.find_params(t.weight.data)
+        t.weight.data = wq.quantize(t.weight.data).to(torch.float16)
+        w.quantizer.configure(bits=8, sym=True, static=True, observer_type="minmax")
+        w.quantizer.calibrate = True
+        for i in range(2):
+            if i == 1:
+                w.quantizer.last_calibrate = True
+            w(rnd(1, 32, K_in))
+        w.quantizer.calibrate = False
+        w.quantizer.quant = True
+        x = rnd(2, 16, K_in)
+        y = w(x.clone())
+        case[f"{tag}_x"] = x.numpy()
+        case[f"{tag}_y"] = y.detach().numpy()
+        case[f"{tag}_act_scale"] = w.quantizer.quantizer.scale.numpy()
+        if split:
+            case[f"{tag}_W"] = torch.cat([w.L1.weight.data.half(), w.L2.weight.data.half()], 1).numpy()
+        else:
+            case[f"{tag}_W"] = w.module.weight.data.numpy()
+        case[f"{tag}_wscale"] = wq.scale.numpy()
+        if bias:
+            case[f"{tag}_b"] = lin.bias.data.numpy()
+    np.savez_compressed(os.path.join(OUT, "wrapper768.npz"), **case)
+
+    # ---------------------------------------------------------------- 10. BASELINE config 1: QWenBlock
+    # One reference decoder layer (model/modeling_qwen_opt.py:390-420) at hidden 4096 / ffn 11008 /
+    # seq 1024 with its 7 ActQuantWrappers (RTN W4, static INT8 minmax, online Hadamard K = 172 on
+    # mlp.c_proj), through oracle/ref_block.py.  The weights are regenerated from per-layer seeds by
+    # the test; the fixture keeps the calibrated scales, the block output and every wrapper's
+    # input / output on sampled token rows.
+    from oracle import ref_block as RB
+    from model import modeling_qwen_opt as mq
+
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    block, wrappers, wscales = RB.build_reference_block(qu, hu, mq)
+    rows = np.unique(np.concatenate([np.arange(0, 4), np.arange(1020, 1024),
+                                     np.random.default_rng(0).integers(4, 1020, 8)]))
+    ridx = torch.from_numpy(rows)
+    case = {"rows": rows, "seed0": np.asarray(RB.SEED0), "calib_seeds": np.asarray([11, 12]),
+            "x_seed": np.asarray(13), "tokens": np.asarray(1024)}
+    with torch.no_grad():
+        RB.calibrate(block, wrappers, mq, [RB.hidden_states(11, 1024), RB.hidden_states(12, 1024)])
+        grabbed = {}
+        hooks = [w.register_forward_hook(lambda m, i, o, n=n: grabbed.__setitem__(n, (i[0], o)))
+                 for n, w in wrappers.items()]
+        y = RB.run_block(block, mq, RB.hidden_states(13, 1024))
+        for h in hooks:
+            h.remove()
+    for n, w in wrappers.items():
+        key = n.replace(".", "_")
+        xi, yo = grabbed[n]
+        case[f"{key}_x"] = xi.reshape(-1, xi.shape[-1])[ridx].numpy()
+        case[f"{key}_y"] = yo.reshape(-1, yo.shape[-1])[ridx].numpy()
+        case[f"{key}_act_scale"] = w.quantizer.quantizer.scale.numpy()
+        case[f"{key}_wscale_sum"] = np.asarray(wscales[n].double().sum().item())
+    case["block_y"] = y[0, ridx].numpy()
+    case["block_y_rownorm"] = y[0].float().norm(dim=-1).numpy()
+    np.savez_compressed(os.path.join(OUT, "qwen_block.npz"), **case)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

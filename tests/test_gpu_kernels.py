@@ -22,6 +22,23 @@ def ops():
     return _ops
 
 
+@pytest.fixture
+def force(ops):
+    """Test-only dispatcher overrides (mq_debug_force_*), reset after the test."""
+    from mquant_b200._lib import lib
+
+    class F:
+        def gemm(self, kernel):
+            lib().mq_debug_force_gemm_kernel({"default": 0, "v2": 3, "v4": 4}[kernel])
+
+        def hadamard_cuda_cores(self, on):
+            lib().mq_debug_force_hadamard_kernel(1 if on else 0)
+
+    yield F()
+    lib().mq_debug_force_gemm_kernel(0)
+    lib().mq_debug_force_hadamard_kernel(0)
+
+
 def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
@@ -256,13 +273,10 @@ def test_hadamard_pow2(ops, n):
 @pytest.mark.parametrize("path", ["default", "simt"])
 @pytest.mark.parametrize("n,n_in", [(11008, 11008), (13824, 13696), (14336, 14336), (19968, 18944),
                                     (5120, 5120), (3584, 3584), (3072, 3072), (5120 * 2, 5120 * 2)])
-def test_hadamard_nonpow2(ops, monkeypatch, path, n, n_in):
+def test_hadamard_nonpow2(ops, force, path, n, n_in):
     """default = FWHT in registers + hadK on tcgen05 (mq_hadamard_tc2.cu; P = 64 .. 512),
     simt = the CUDA-core kernel."""
-    if path == "simt":
-        monkeypatch.setenv("MQ_HAD_SIMT", "1")
-    else:
-        monkeypatch.delenv("MQ_HAD_SIMT", raising=False)
+    force.hadamard_cuda_cores(path == "simt")
     k = O.get_hadK(n)[1]
     assert k > 1
     rng = np.random.default_rng(n)
@@ -278,11 +292,9 @@ def test_hadamard_nonpow2(ops, monkeypatch, path, n, n_in):
 
 @pytest.mark.parametrize("n,n_in,M", [(11008, 11008, 9), (11008, 11008, 300), (13824, 13696, 5),
                                       (19968, 18944, 7), (5120, 5120, 33), (3584, 3584, 130)])
-@pytest.mark.parametrize("kernel", ["tc2", "tc1"])
-def test_hadamard_nonpow2_tensor_core_path(ops, monkeypatch, kernel, n, n_in, M):
-    """codes-only requests on the tensor-core kernels (tc2 = default: FWHT in registers + hadK on
-    tcgen05; tc1 = both Kronecker factors on tcgen05, n/had_k in {64,128}); compare with the
-    CUDA-core kernel and with the oracle."""
+def test_hadamard_nonpow2_tensor_core_path(ops, force, n, n_in, M):
+    """codes-only requests on the tensor-core kernel (FWHT in registers + hadK on tcgen05); compare
+    with the CUDA-core kernel and with the oracle."""
     from mquant_b200 import hadamard_utils as hu
 
     k = O.get_hadK(n)[1]
@@ -295,16 +307,13 @@ def test_hadamard_nonpow2_tensor_core_path(ops, monkeypatch, kernel, n, n_in, M)
     scales = ops.make_scales(float(s), float(s_vis), "cuda")
     xd, md = dev(x), dev(mod)
     for split in (False, True):
-        monkeypatch.delenv("MQ_HAD_SIMT", raising=False)
-        if kernel == "tc1":
-            monkeypatch.setenv("MQ_HAD_KERNEL", "tc1")
+        force.hadamard_cuda_cores(False)
         tc = ops.hadamard(xd, had_k=k, hadk=hk, n=n, scales=scales, modality=md, want_codes=True,
                           want_f16=False, split=split)
-        monkeypatch.delenv("MQ_HAD_KERNEL", raising=False)
-        monkeypatch.setenv("MQ_HAD_SIMT", "1")
+        force.hadamard_cuda_cores(True)
         ref = ops.hadamard(xd, had_k=k, hadk=hk, n=n, scales=scales, modality=md, want_codes=True,
                            want_f16=True, split=split)  # CUDA-core kernel
-        monkeypatch.delenv("MQ_HAD_SIMT", raising=False)
+        force.hadamard_cuda_cores(False)
         q_tc, q_ref = host(tc["q"]).astype(np.int32), host(ref["q"]).astype(np.int32)
         d = np.abs(q_tc - q_ref)
         assert d.max() <= 1, d.max()
@@ -480,7 +489,7 @@ def test_gemm_simt_matches_oracle(ops, M, N, K, per_row, bias, split):
     assert np.array_equal(bits16(O.qlinear_int(qa, s_a, cw, s_w, b, x0, w0)), bits16(oracle_gemm(case)))
 
 
-@pytest.mark.parametrize("kernel", ["default", "v1", "v2", "v3", "v4", "2cta"])
+@pytest.mark.parametrize("kernel", ["default", "v2", "v4"])
 @pytest.mark.parametrize("M,N,K,per_row,bias,split", [
     (128, 256, 128, False, False, False),     # one tile, one k-block
     (128, 256, 512, False, False, False),     # pipeline wraps once
@@ -491,13 +500,10 @@ def test_gemm_simt_matches_oracle(ops, M, N, K, per_row, bias, split):
     (600, 768, 640, True, True, True),        # 256-row tiles: last tile's second half is all padding
     (5000, 1024, 2048, True, False, False),   # many tiles per CTA, ragged M
 ])
-def test_gemm_tcgen05_matches_oracle(ops, monkeypatch, kernel, M, N, K, per_row, bias, split):
-    """Every tcgen05 kernel generation (the default and the opt-in ones kept for comparison) is
-    bit-exact against the oracle."""
-    if kernel != "default":
-        monkeypatch.setenv("MQ_GEMM_KERNEL", kernel)
-    else:
-        monkeypatch.delenv("MQ_GEMM_KERNEL", raising=False)
+def test_gemm_tcgen05_matches_oracle(ops, force, kernel, M, N, K, per_row, bias, split):
+    """The dispatcher's choice and each of the two persistent tcgen05 kernels forced onto every
+    shape (128 x 256 and 256 x 256 tiles) are bit-exact against the oracle."""
+    force.gemm(kernel)
     case = gemm_case(np.random.default_rng(M * 3 + N + K), M, N, K, per_row, bias, split)
     got = run_gemm(ops, case, simt=False)
     assert np.array_equal(bits16(got), bits16(oracle_gemm(case)))
@@ -537,6 +543,124 @@ def test_gemm_split_k_path(ops, M, N, K, per_row, bias, split):
         case = gemm_case(rng, M, N, K, per_row, bias, split)
         got = run_gemm(ops, case, simt=False)
         assert np.array_equal(bits16(got), bits16(oracle_gemm(case))), rep
+
+
+# The shapes the headline benchmark runs (bench.py: Qwen-VL-Chat prefill, 16384 tokens per step; q|k|v
+# and w1|w2 fused) plus the GLM-4V widths of BASELINE config 5 (13696 -> K padded to 13824).
+BENCH_SHAPES = [(4096, 4096), (4096, 12288), (4096, 22016), (11008, 4096), (13824, 4096), (4096, 13696)]
+
+
+@pytest.mark.parametrize("K,N", BENCH_SHAPES)
+def test_gemm_default_dispatch_at_benchmark_shapes(ops, K, N):
+    """M = 16384 through the DEFAULT dispatcher (must pick the 256 x 256 kernel: 64 m-tiles x up to
+    86 n-tiles x up to 108 k-blocks per launch), per-row scales + bias (+ split rank-1 term), checked
+    bit for bit against the exact integer oracle on 640 sampled rows x all columns."""
+    from mquant_b200._lib import lib
+
+    M = 16384
+    split = N == 4096 and K == 11008
+    assert lib().mq_w4a8_gemm_plan(M, N, K, lib().mq_w4a8_gemm_workspace_bytes(M, N, K)) == 4
+    g = torch.Generator(device="cuda").manual_seed(K * 7 + N)
+    qa = torch.randint(-128, 128, (M, K), dtype=torch.int8, device="cuda", generator=g)
+    cw = torch.randint(-8, 8, (N, K), dtype=torch.int8, device="cuda", generator=g)
+    s_a = torch.rand(M, device="cuda", generator=g) * 0.05 + 0.01
+    s_w = torch.rand(N, device="cuda", generator=g) * 0.01 + 0.001
+    bias = (torch.randn(N, device="cuda", generator=g) * 0.5).half()
+    x0 = w0 = None
+    if split:
+        qa[:, 0] = 0
+        cw[:, 0] = 0
+        x0 = (torch.randn(M, device="cuda", generator=g) * 30).half()
+        w0 = (torch.randn(N, device="cuda", generator=g) * 0.02).half()
+    out = ops.w4a8_gemm(qa, ops.pack_w4(cw), s_a, s_w, N, bias=bias, x0=x0, w0=w0)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(N + K)
+    rows = np.unique(np.concatenate([np.arange(0, 64), np.arange(M - 64, M), np.arange(8128, 8256),
+                                     rng.integers(0, M, 400)]))
+    ridx = torch.from_numpy(rows).cuda()
+    case = (host(qa[ridx]), host(cw), host(s_a[ridx]), host(s_w), host(bias),
+            None if x0 is None else host(x0[ridx]), None if w0 is None else host(w0))
+    want = oracle_gemm(case)
+    got = host(out[ridx])
+    assert np.array_equal(bits16(got), bits16(want)), int((bits16(got) != bits16(want)).sum())
+    # every row that was not sampled: a cheap whole-matrix property (finite, and the column sums of
+    # the sampled block are reproduced when the GEMM is re-run on the sampled rows alone)
+    assert bool(torch.isfinite(out).all())
+    again = ops.w4a8_gemm(qa[ridx].contiguous(), ops.pack_w4(cw), s_a[ridx].contiguous(), s_w, N, bias=bias,
+                          x0=None if x0 is None else x0[ridx].contiguous(), w0=w0)
+    assert torch.equal(again, out[ridx])
+
+
+def test_gemm_seeded_fuzz(ops):
+    """A seeded slice of tools/fuzz.py inside the suite: random shapes (K up to 19968, ragged M and N)
+    through the dispatcher against the CUDA-core kernel, bit-exact."""
+    rng = np.random.default_rng(2026)
+    for it in range(40):
+        K = 128 * int(rng.integers(1, 157))
+        N = 8 * int(rng.integers(1, 400))
+        M = int(rng.choice([1, 3, 17, 64, 129, 300, 777, 1500]))
+        if it % 8 == 0:
+            K, N, M = 19968, 8 * int(rng.integers(30, 200)), int(rng.choice([5, 130, 520]))
+        case = gemm_case(rng, M, N, K, bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2)))
+        got, ref = run_gemm(ops, case, simt=False), run_gemm(ops, case, simt=True)
+        assert np.array_equal(bits16(got), bits16(ref)), (M, N, K)
+
+
+@pytest.mark.parametrize("n,n_in", [(4096, 4096), (8192, 8192), (11008, 11008), (13824, 13696), (19968, 18944)])
+def test_hadamard_at_benchmark_rows(ops, force, n, n_in):
+    """M = 16384 with the benchmark's outlier distribution: the fused kernel against the CUDA-core
+    kernel on every row (codes within +-1, rare) and against the oracle on 96 sampled rows."""
+    from mquant_b200 import hadamard_utils as hu
+
+    M = 16384
+    k = O.get_hadK(n)[1]
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.randn(M, n_in, device="cuda", generator=g) * 3
+    x[:, 7] *= 40
+    x[:, n_in // 2 + 3] *= 25
+    x = x.half()
+    s = float(torch.tensor(float(x.abs().max()) / 127 / 4, dtype=torch.float16))
+    s_vis = float(torch.tensor(s * 2.5, dtype=torch.float16))
+    mod = (torch.rand(M, device="cuda", generator=g) < 0.4).to(torch.uint8)
+    scales = ops.make_scales(s, s_vis, "cuda")
+    hk = hu.hadK_device(k, "cuda") if k > 1 else None
+    fast = ops.hadamard(x, had_k=k, hadk=hk, n=n, scales=scales, modality=mod, want_codes=True, want_f16=False)
+    force.hadamard_cuda_cores(True)
+    slow = ops.hadamard(x, had_k=k, hadk=hk, n=n, scales=scales, modality=mod, want_codes=True, want_f16=False)
+    force.hadamard_cuda_cores(False)
+    d = (fast["q"].int() - slow["q"].int()).abs()
+    assert int(d.max()) <= 1
+    assert float((d > 0).float().mean()) < 2e-3
+    assert torch.equal(fast["s_row"], slow["s_row"])
+    rows = np.concatenate([np.arange(0, 32), np.arange(M - 32, M), np.random.default_rng(n).integers(0, M, 32)])
+    ridx = torch.from_numpy(rows).cuda()
+    ref = O.matmul_hadU_cuda(O.pad_last(host(x[ridx]), n))
+    oc = O.msq_quant_codes(ref, host(mod[ridx]), np.float32(s), np.float32(s_vis)).astype(np.int32)
+    d = np.abs(host(fast["q"][ridx]).astype(np.int32) - oc)
+    assert d.max() <= 1
+    assert (d > 0).mean() < 2e-3, (d > 0).mean()
+
+
+@pytest.mark.parametrize("n", [64, 256, 1024, 4096, 8192])
+def test_hadamard_transform_seam(ops, n):
+    """mq_hadamard_transform_f16 == fast_hadamard_transform.hadamard_transform(x, scale): any scale,
+    strided leading dims (the reference calls it on a transposed view, quant_utils.py:351)."""
+    from mquant_b200.fht import hadamard_transform
+
+    rng = np.random.default_rng(n)
+    x = rnd_act(rng, 50, n)
+    for scale in (1.0, 1.0 / np.sqrt(n), 0.37):
+        y = host(hadamard_transform(dev(x).reshape(5, 10, n), scale))
+        ref = O.fht(x, np.float32(scale)).reshape(5, 10, n)
+        d = np.abs(bits16(y).astype(np.int32) - bits16(ref).astype(np.int32))
+        a = np.abs(y.astype(np.float32) - ref.astype(np.float32))
+        rms = np.sqrt((ref.astype(np.float32) ** 2).mean())
+        assert np.all((d <= 1) | (a <= 1e-4 * rms)), (n, scale, d.max())
+    # fp32 / odd sizes: the torch butterfly (offline weight rotation), zero padded like the original
+    w = torch.randn(7, 96, device="cuda")
+    yw = host(hadamard_transform(w, 0.5))
+    refw = O.fwht_last(np.pad(host(w).astype(np.float64), ((0, 0), (0, 32))))[:, :96] * 0.5
+    assert np.allclose(yw, refw, atol=1e-4)
 
 
 def test_gemm_extreme_codes(ops):

@@ -47,13 +47,16 @@ def build_wrapper(qu, g, tag, K_in, N_out, had, split):
     return w
 
 
-CASES = [("plain", 256, 128, False, False), ("had256", 256, 64, True, False)]
+# wrapper.npz also holds had344 / split (344 = 172 x 2): n / had_k = 2 is below what the CUDA kernels
+# take (>= 64; no model has such a layer) -- the same two configurations run at K = 768 = 12 x 64
+CASES = [("wrapper", "plain", 256, 128, False, False), ("wrapper", "had256", 256, 64, True, False),
+         ("wrapper768", "had768", 768, 64, True, False), ("wrapper768", "split768", 768, 64, True, True)]
 
 
-@pytest.mark.parametrize("tag,K_in,N_out,had,split", CASES)
+@pytest.mark.parametrize("gname,tag,K_in,N_out,had,split", CASES)
 @torch.no_grad()
-def test_wrapper_fake_and_real_paths(qu, golden, tag, K_in, N_out, had, split):
-    g = golden("wrapper")
+def test_wrapper_fake_and_real_paths(qu, golden, gname, tag, K_in, N_out, had, split):
+    g = golden(gname)
     w = build_wrapper(qu, g, tag, K_in, N_out, had, split)
     x = torch.from_numpy(g[f"{tag}_x"]).cuda()
     ref = g[f"{tag}_y"]
@@ -72,12 +75,20 @@ def test_wrapper_fake_and_real_paths(qu, golden, tag, K_in, N_out, had, split):
     s_w = g[f"{tag}_wscale"].reshape(-1)
     xr = x2
     if had:
-        from mquant_b200 import ops
-        xr = ops.hadamard(torch.from_numpy(x2).cuda(), n=K_in)["y"].cpu().numpy()
+        from mquant_b200 import hadamard_utils as hu, ops
+        k = O.get_hadK(K_in)[1]
+        xr = ops.hadamard(torch.from_numpy(x2).cuda(), had_k=k, hadk=hu.hadK_device(k, "cuda") if k > 1 else None,
+                          n=K_in)["y"].cpu().numpy()
     ca = O.act_quant_codes(xr, s_a)
-    cw = np.rint(g[f"{tag}_W"].astype(np.float32) / s_w[:, None]).astype(np.int8)
+    W = g[f"{tag}_W"].astype(np.float32)
+    cw = np.rint(W / s_w[:, None]).astype(np.int8)
     b = g[f"{tag}_b"] if f"{tag}_b" in g.files else None
-    want = O.qlinear_int(ca, s_a, cw, s_w, b)
+    x0 = w0 = None
+    if split:  # channel 0 bypasses the quantiser: fp16 x0 * w0 rank-1 term (quant_utils.py:367-376)
+        x0, w0 = xr[:, 0].copy(), g[f"{tag}_W"][:, 0].copy()
+        ca[:, 0] = 0
+        cw[:, 0] = 0
+    want = O.qlinear_int(ca, s_a, cw, s_w, b, x0, w0)
     assert np.array_equal(y_real.reshape(want.shape).view(np.uint16), want.view(np.uint16))
 
 
@@ -123,6 +134,97 @@ def test_qwenvl_mlp_down_proj_layer(qu):
         cos, err = cos_maxabs(y_real.cpu().numpy(), y_fake.cpu().numpy())
         assert cos >= 0.9999, (split, cos, err)
         assert err <= 2.0 ** -9 * float(y_fake.abs().max()) * 4, (split, err)
+
+
+def _our_block(qu, g, dtype=torch.float16):
+    """The 7 Linears of BASELINE config 1 through the drop-in API (weights regenerated from the
+    fixture's seeds, RTN W4 by our WeightQuantizer, static scales from the fixture)."""
+    from mquant_b200 import hadamard_utils as hu
+    from oracle import ref_block as RB
+
+    wr, wq_scales = {}, {}
+    for i, (name, K_in, N_out, bias) in enumerate(RB.LINEARS):
+        W, b = RB.linear_weights(i, K_in, N_out, bias, dtype)
+        lin = torch.nn.Linear(K_in, N_out, bias=bias).to(dtype).cuda()
+        lin.weight.data = W.cuda()
+        if bias:
+            lin.bias.data = b.cuda()
+        if name == "mlp.c_proj":
+            hu.apply_exact_had_to_linear(lin, had_dim=-1, output=False)
+        w = qu.ActQuantWrapper(lin)
+        if name == "mlp.c_proj":
+            w.online_full_had = True
+            w.had_K, w.K = hu.get_hadK(K_in)
+        wq = qu.WeightQuantizer()
+        wq.configure(4, perchannel=True, sym=True, mse=False)
+        wq.find_params(lin.weight.data)
+        lin.weight.data = wq.quantize(lin.weight.data).to(dtype)
+        w.quantizer.configure(bits=8, sym=True, static=True, observer_type="minmax")
+        w.quantizer.quantizer.set_scales(torch.from_numpy(g[name.replace(".", "_") + "_act_scale"]).cuda())
+        w.quantizer.quant = True
+        wr[name], wq_scales[name] = w, wq.scale
+    return wr, wq_scales
+
+
+@torch.no_grad()
+def test_qwen_block_wrappers_match_reference(qu, golden):
+    """BASELINE config 1, wrapper by wrapper: the reference's own QWenBlock forward (hidden 4096,
+    ffn 11008, seq 1024; fixture from oracle/gen_golden.py section 10) recorded every wrapper's input
+    and output on 16 token rows -- real post-RMSNorm / post-attention / SiLU-gated distributions.
+    Feeding the recorded inputs to the integer path must reproduce the recorded outputs."""
+    g = golden("qwen_block")
+    wr, wq_scales = _our_block(qu, g)
+    for name, w in wr.items():
+        key = name.replace(".", "_")
+        # same RTN scales as the reference computed (checksum of the per-channel scales)
+        assert abs(float(wq_scales[name].double().sum()) - float(g[key + "_wscale_sum"])) < 1e-9 * max(1.0, abs(float(g[key + "_wscale_sum"])))
+        x = torch.from_numpy(g[key + "_x"]).cuda()
+        ref = g[key + "_y"]
+        y_fake = w(x.clone()).cpu().numpy()
+        w.freeze(wq_scales[name], check=True)
+        y_real = w(x.clone()).cpu().numpy()
+        for tag, y in (("fake", y_fake), ("real", y_real)):
+            cos, err = cos_maxabs(y, ref)
+            assert cos >= 0.9999, (name, tag, cos)
+            assert err <= 4 * 2.0 ** -9 * np.abs(ref).max() + 1e-3, (name, tag, err, np.abs(ref).max())
+
+
+@torch.no_grad()
+def test_qwen_block_output_matches_reference(qu, golden):
+    """BASELINE config 1, whole layer: RMSNorm -> q/k/v -> causal attention -> c_proj -> residual ->
+    RMSNorm -> w1, w2 -> a1 * silu(a2) -> online Hadamard -> c_proj -> residual (model/
+    modeling_qwen_opt.py:176-210, 293-367, 390-470) with the 7 Linears on the INTEGER path, against
+    the reference block's output: cosine and max-abs reported and asserted."""
+    from oracle import ref_block as RB
+
+    g = golden("qwen_block")
+    wr, wq_scales = _our_block(qu, g)
+    for name, w in wr.items():
+        w.freeze(wq_scales[name], check=True)
+    x = RB.hidden_states(int(g["x_seed"]), int(g["tokens"])).cuda()
+    T, H, nh = x.shape[1], RB.HIDDEN, RB.HEADS
+
+    def rms(v):  # modeling_qwen_opt.py:1260-1274 (weight = ones)
+        vf = v.float()
+        return (vf * torch.rsqrt(vf.pow(2).mean(-1, keepdim=True) + 1e-6)).type_as(v)
+
+    h = rms(x)
+    q, k, v = (wr[n](h).view(1, T, nh, H // nh).permute(0, 2, 1, 3) for n in ("attn.q_proj", "attn.k_proj", "attn.v_proj"))
+    att = torch.matmul(q, k.transpose(-1, -2)) / torch.full([], (H // nh) ** 0.5, dtype=q.dtype, device=q.device)
+    att = att + torch.full((T, T), torch.finfo(x.dtype).min, dtype=x.dtype, device="cuda").triu(1)
+    att = torch.softmax(att, dim=-1).type(v.dtype)
+    ctx = torch.matmul(att, v).transpose(1, 2).contiguous().view(1, T, H)
+    r = x + wr["attn.c_proj"](ctx)
+    h2 = rms(r)
+    y = r + wr["mlp.c_proj"](wr["mlp.w1"](h2) * torch.nn.functional.silu(wr["mlp.w2"](h2)))
+    rows = torch.from_numpy(g["rows"]).cuda()
+    cos, err = cos_maxabs(y[0, rows].cpu().numpy(), g["block_y"])
+    print(f"QWenBlock W4A8 integer path vs reference fake-quant fp16: cos {cos:.7f}, max-abs {err:.4f} "
+          f"(max|y| {np.abs(g['block_y']).max():.2f})")
+    assert cos >= 0.9999, cos
+    assert err <= 8 * 2.0 ** -9 * np.abs(g["block_y"]).max(), err
+    rn = y[0].float().norm(dim=-1).cpu().numpy()
+    assert np.allclose(rn, g["block_y_rownorm"], rtol=5e-3), float(np.abs(rn / g["block_y_rownorm"] - 1).max())
 
 
 @pytest.mark.parametrize("model,had_name,k_in,k_pad,had_k", [

@@ -205,3 +205,53 @@ def test_fuse_siblings_gating(built):
     unfrozen = wrapper(256)
     unfrozen.real_quant = False
     assert qu.fuse_siblings([wrapper(256), unfrozen]) is None
+
+
+def test_update_all_quantization_params_equals_per_wrapper_update():
+    """One host round trip for all wrappers == the per-wrapper update (which mirrors the reference's
+    MinmaxObserver.get_quantization_params): statistics installed as the kernels leave them, text-only,
+    visual-only, both, bf16 statistics, an uncalibrated wrapper."""
+    import copy
+
+    import torch
+
+    from mquant_b200 import quant_utils as qu
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.c = (torch.nn.Linear(16, 8) for _ in range(3))
+            self.d, self.e = torch.nn.Linear(16, 8), torch.nn.Linear(16, 8)
+
+    net = Net()
+    qu.add_actquant(net)
+    cfg = {"a": (True, (-1.5, 2.0), (-8.0, 6.0), [10, 4], torch.float16),
+           "b": (True, (-0.3, 0.0), None, [7, 0], torch.float16),
+           "c": (True, None, (-2.0, 9.0), [0, 5], torch.float16),
+           "d": (False, (-100.0, 31.0), None, None, torch.bfloat16),
+           "e": (False, None, None, None, torch.float16)}
+    for name, (msq, text, vis, seen, dt) in cfg.items():
+        q = getattr(net, name).quantizer
+        q.configure(bits=8, sym=True, static=True, observer_type="minmax", msq=msq)
+        for o, st in ((q.observer, text), (q.observer_visual, vis)):
+            if st is not None:
+                o.state = torch.tensor(st, dtype=torch.float32)
+                o._dtype, o._channels = dt, 16
+        if seen is not None:
+            q._seen = torch.tensor(seen, dtype=torch.int32)
+    ref = copy.deepcopy(net)
+    for name in cfg:
+        q = getattr(ref, name).quantizer
+        if qu._observed(q.observer) or (q.msq and qu._observed(q.observer_visual)):
+            q.update_quantization_params()
+    n = qu.update_all_quantization_params(net)
+    assert n == 4
+    for name in cfg:
+        a, b = getattr(net, name).quantizer.quantizer, getattr(ref, name).quantizer.quantizer
+        for attr in ("scale", "scale_visual"):
+            x, y = getattr(a, attr), getattr(b, attr)
+            assert (x is None) == (y is None), (name, attr)
+            if x is not None:
+                assert x.dtype == y.dtype and torch.equal(x.reshape(()), y.reshape(())), (name, attr, x, y)
+        if a.scale is not None:
+            assert torch.equal(a.device_scales(torch.device("cpu")), b.device_scales(torch.device("cpu"))), name

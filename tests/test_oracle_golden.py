@@ -138,13 +138,17 @@ def test_matmul_hadU_cuda_rounding_points(golden):
             assert (d > 0).mean() < 5e-3, (n, key, (d > 0).mean())
 
 
-@pytest.mark.parametrize("tag", ["plain", "had256", "had344", "split"])
-def test_wrapper_forward(golden, tag):
-    g = golden("wrapper")
+WRAPPER_CASES = [("wrapper", "plain"), ("wrapper", "had256"), ("wrapper", "had344"), ("wrapper", "split"),
+                 ("wrapper768", "had768"), ("wrapper768", "split768")]
+
+
+@pytest.mark.parametrize("gname,tag", WRAPPER_CASES)
+def test_wrapper_forward(golden, gname, tag):
+    g = golden(gname)
     x = g[f"{tag}_x"]
     b = g[f"{tag}_b"] if f"{tag}_b" in g.files else None
     y = O.qlinear_fake(x, g[f"{tag}_W"], b, g[f"{tag}_act_scale"], online_had=tag != "plain",
-                       split=tag == "split")
+                       split=tag.startswith("split"))
     ref = g[f"{tag}_y"].astype(np.float32)
     err = np.abs(y.astype(np.float32) - ref).max()
     cos = (y.astype(np.float64) * ref).sum() / np.sqrt((y.astype(np.float64) ** 2).sum() * (ref.astype(np.float64) ** 2).sum())
@@ -152,11 +156,11 @@ def test_wrapper_forward(golden, tag):
     assert err <= 2.0 ** -9 * np.abs(ref).max() + 1e-3, err
 
 
-@pytest.mark.parametrize("tag", ["plain", "had256", "had344", "split"])
-def test_int_path_matches_fake_quant_within_tolerance(golden, tag):
+@pytest.mark.parametrize("gname,tag", WRAPPER_CASES)
+def test_int_path_matches_fake_quant_within_tolerance(golden, gname, tag):
     """the real-integer layer differs from the reference's fake-quant fp16 layer
     only by fp16 rounding of dequantised operands: cos >= 0.9999, max-abs <= 2^-9 max|y|."""
-    g = golden("wrapper")
+    g = golden(gname)
     x = g[f"{tag}_x"].reshape(-1, g[f"{tag}_x"].shape[-1])
     if tag != "plain":
         x = O.matmul_hadU_cuda(x)
@@ -164,7 +168,7 @@ def test_int_path_matches_fake_quant_within_tolerance(golden, tag):
     s_w = g[f"{tag}_wscale"].reshape(-1)
     s_a = np.float32(g[f"{tag}_act_scale"])
     b = g[f"{tag}_b"] if f"{tag}_b" in g.files else None
-    if tag == "split":
+    if tag.startswith("split"):
         cw = np.rint(W[:, 1:].astype(np.float32) / s_w[:, None]).astype(np.int8)
         cw = np.concatenate([np.zeros((cw.shape[0], 1), np.int8), cw], 1)
         ca = O.act_quant_codes(x, s_a)

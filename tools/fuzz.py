@@ -13,6 +13,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mquant_b200 import hadamard_utils as hu, ops  # noqa: E402
+from mquant_b200._lib import lib  # noqa: E402
 
 
 def main():
@@ -61,12 +62,12 @@ def main():
         mod = (torch.rand(M, device="cuda", generator=g) < 0.4).to(torch.uint8)
         scales = ops.make_scales(0.07 + 0.01 * ri(0, 9), 0.2 + 0.01 * ri(0, 9), "cuda")
         split = bool(ri(0, 1))
-        os.environ.pop("MQ_HAD_SIMT", None)
+        lib().mq_debug_force_hadamard_kernel(0)
         r = ops.hadamard(x, had_k=K_, hadk=hk, n=n, scales=scales, modality=mod, want_codes=True, want_f16=bool(ri(0, 1)),
                          split=split)
-        os.environ["MQ_HAD_SIMT"] = "1"
+        lib().mq_debug_force_hadamard_kernel(1)
         s = ops.hadamard(x, had_k=K_, hadk=hk, n=n, scales=scales, modality=mod, want_codes=True, want_f16=True, split=split)
-        os.environ.pop("MQ_HAD_SIMT", None)
+        lib().mq_debug_force_hadamard_kernel(0)
         d = (r["q"].int() - s["q"].int()).abs()
         if int(d.max()) > 1 or float((d > 0).float().mean()) > 3e-3:
             hbad += 1

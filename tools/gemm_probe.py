@@ -7,6 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mquant_b200._lib import lib  # noqa: E402
 from mquant_b200 import ops  # noqa: E402
 from tools.microbench import timeit  # noqa: E402
 
@@ -26,7 +27,7 @@ def main():
         s_w = torch.rand(N, device="cuda") * 0.01
         out = torch.empty(M, N, dtype=torch.float16, device="cuda")
         for k in a.kernels.split(","):
-            os.environ["MQ_GEMM_KERNEL"] = k
+            lib().mq_debug_force_gemm_kernel({"v2": 3, "v4": 4}.get(k, 0))
             for mask in a.masks.split(","):
                 os.environ["MQ_GEMM_DEBUG"] = mask
                 sec, best = timeit(lambda: ops.w4a8_gemm(q, w4, s_a, s_w, N, out=out), flush=True)

@@ -20,7 +20,6 @@ def main():
     ap.add_argument("--timeline", type=int, default=-1, help="MQ_HAD_DEBUG mask to run with bit 256 and dump stamps")
     a = ap.parse_args()
     if a.kernel:
-        os.environ["MQ_HAD_KERNEL"] = a.kernel
     hk_, K = hu.get_hadK(a.n)
     hk = hu.hadK_device(K, "cuda")
     x = (torch.randn(a.M, a.n, device="cuda") * 3).half()

@@ -10,6 +10,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mquant_b200._lib import lib  # noqa: E402
 from mquant_b200 import ops  # noqa: E402
 
 
@@ -31,9 +32,9 @@ def main():
             out = torch.empty(M, N, dtype=torch.float16, device="cuda")
             for kern in a.kernels.split(","):
                 if kern == "default":
-                    os.environ.pop("MQ_GEMM_KERNEL", None)
+                    lib().mq_debug_force_gemm_kernel(0)
                 else:
-                    os.environ["MQ_GEMM_KERNEL"] = kern
+                    lib().mq_debug_force_gemm_kernel({"v2": 3, "v4": 4}.get(kern, 0))
                 for i in range(R):
                     ops.w4a8_gemm(q, w4s[i], s_a, s_w, N, out=out)
                 torch.cuda.synchronize()
@@ -48,7 +49,7 @@ def main():
                 print(json.dumps({"kernel": kern, "M": M, "K": K, "N": N, "us_per_launch": round(us, 2),
                                   "weight_GBps": round(N * K / 2 / us / 1e3, 1), "TOPs": round(2 * M * N * K / us / 1e6, 1)}),
                       flush=True)
-        os.environ.pop("MQ_GEMM_KERNEL", None)
+        lib().mq_debug_force_gemm_kernel(0)
         del w4s
 
 

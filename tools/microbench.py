@@ -60,7 +60,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--only", default="")
     a = ap.parse_args()
-    from mquant_b200 import hadamard_utils as hu, ops
+    from mquant_b200 import _lib, hadamard_utils as hu, ops
 
     hbm, bf16, src = peaks()
     print(f"peaks ({src}): HBM {hbm:.0f} GB/s, bf16 {bf16:.0f} TFLOP/s; INT8 nominal 4500 TOP/s")
@@ -156,7 +156,7 @@ def main():
                 s_a = torch.rand(M, device="cuda") * 0.1
                 s_w = torch.rand(N, device="cuda") * 0.01
                 out = torch.empty(M, N, dtype=torch.float16, device="cuda")
-                kname = os.environ.get("MQ_GEMM_KERNEL", "default")
+                kname = "default"
                 sec, best = timeit(lambda: ops.w4a8_gemm(q, w4, s_a, s_w, N, out=out), flush=True)
                 rec(f"w4a8_gemm[{kname}]", f"M{M} K{K} N{N}", sec, best,
                     bytes_=N * K // 2 + M * K + 2 * M * N + 4 * N, ops_=2 * M * N * K)
@@ -171,14 +171,11 @@ def main():
                 s_a = torch.rand(M, device="cuda") * 0.1
                 out = torch.empty(M, N, dtype=torch.float16, device="cuda")
                 for name, env in (("w4a8_gemv", None), ("w4a8_gemm_tc", "v2")):
-                    if env:
-                        os.environ["MQ_GEMM_KERNEL"] = env
-                    else:
-                        os.environ.pop("MQ_GEMM_KERNEL", None)
+                    _lib.lib().mq_debug_force_gemm_kernel(3 if env else 0)
                     sec, best = timeit(lambda: ops.w4a8_gemm(q, w4, s_a, s_w, N, out=out), flush=True, iters=20)
                     rec(name, f"M{M} K{K} N{N}", sec, best, bytes_=N * K // 2 + M * K + 2 * M * N + 4 * N,
                         ops_=2 * M * N * K)
-                os.environ.pop("MQ_GEMM_KERNEL", None)
+                _lib.lib().mq_debug_force_gemm_kernel(0)
         # event-timing floor: an empty-ish launch after the L2 flush
         z = torch.zeros(32, device="cuda")
         sec, best = timeit(lambda: z.add_(1.0), flush=True, iters=20)
