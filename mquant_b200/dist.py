@@ -38,6 +38,10 @@ def _minmax_observers(model):
 
 def pack_minmax(states):
     """[{min..., max...}] fp32 buffers -> one flat [max ; -min] buffer (so a single MAX merges both)."""
+    if states and all(st.numel() == 2 for st in states):
+        # layer-wise observers (the drivers' configuration): three kernels for any number of them
+        sign = torch.tensor([-1.0, 1.0], device=states[0].device)
+        return (torch.stack(states) * sign).flip(1).reshape(-1)  # rows {max, -min}
     parts = []
     for st in states:
         half = st.numel() // 2
@@ -47,6 +51,11 @@ def pack_minmax(states):
 
 
 def unpack_minmax(flat, states):
+    if states and all(st.numel() == 2 for st in states):
+        sign = torch.tensor([-1.0, 1.0], device=flat.device)
+        rows = flat.view(-1, 2).flip(1) * sign  # back to {min, max}
+        torch._foreach_copy_(list(states), list(rows.unbind(0)))
+        return
     off = 0
     for st in states:
         half = st.numel() // 2
@@ -122,14 +131,16 @@ def merge_calibration(model, group=None, channels_hint=None):
         live.append(o)
     if distributed:
         states = [o.state for o in live]
-        seen = [q._seen.to(torch.float32) for q in msq_quantizers]  # exact below 2^24 rows
-        flat = torch.cat([pack_minmax(states)] + seen).contiguous()
+        seen = torch.cat([q._seen for q in msq_quantizers]).to(torch.float32) if msq_quantizers else \
+            torch.zeros(0, device=dev)  # exact below 2^24 rows
+        flat = torch.cat([pack_minmax(states), seen]).contiguous()
         dist.all_reduce(flat, op=dist.ReduceOp.MAX, group=group)  # the ONE data-path collective
         n_stats = sum(s.numel() for s in states)
         unpack_minmax(flat[:n_stats], states)
-        for i, q in enumerate(msq_quantizers):
+        if msq_quantizers:
             # (the MAX over ranks of the row counts: "seen anywhere" is all the scales depend on)
-            q._seen.copy_(flat[n_stats + 2 * i:n_stats + 2 * i + 2].to(torch.int32))
+            merged = flat[n_stats:].to(torch.int32).view(-1, 2)
+            torch._foreach_copy_([q._seen for q in msq_quantizers], list(merged.unbind(0)))
     for o in live:
         o._refresh()
     # the scales were last derived from rank-local statistics: recompute them from the merged ones

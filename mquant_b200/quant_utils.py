@@ -134,6 +134,7 @@ class ActQuantizer(torch.nn.Module):
         assert 0 < self.clip_ratio <= 1, "Clip ratio should be in (0, 1]"
         self.static = static
         self.msq = bool(msq) and static
+        self._fast_obs = None
         if self.static:
             bit_type_a = BIT_TYPE_DICT[f"int{bits}"]  # KeyError for unsupported widths, as the reference
             self.observer = build_observer(observer_type, "activation", bit_type_a, calibration_mode)
@@ -152,6 +153,22 @@ class ActQuantizer(torch.nn.Module):
         return msq.current_modality(ntok, x.device)
 
     def _observe(self, x):
+        # Lean path for the common calibration call (fused MSQ min/max, fp16, states allocated):
+        # calibration of ~1000-token samples is bound by the host cost of a wrapper call, not by the
+        # 3 us kernel -- skip the generic argument plumbing of ops.* (pointers cached once).
+        fast = getattr(self, "_fast_obs", None)
+        if fast is not None and x.dtype is torch.float16 and x.is_cuda and x.is_contiguous():
+            mask = getattr(msq._state, "mask", None)
+            C = x.shape[-1]
+            if (mask is not None and mask.device == x.device and mask.numel() * C == x.numel()
+                    and C == fast[0] and x.device.index == torch.cuda.current_device()
+                    and self.observer.state is fast[5] and self.observer_visual.state is fast[6]
+                    and self._seen is fast[7]):  # (somebody may have installed other statistics)
+                rc = fast[1](x.data_ptr(), C, mask.numel(), C, mask.data_ptr(), fast[2], fast[3], fast[4],
+                             torch.cuda.current_stream().cuda_stream)
+                if rc != 0:
+                    ops.check(rc, "mq_observer_minmax_msq")
+                return
         mod = self._modality(x)
         if mod is None:
             self.observer.update(x)
@@ -172,6 +189,10 @@ class ActQuantizer(torch.nn.Module):
             if getattr(self, "_seen", None) is None:
                 self._seen = torch.zeros(2, dtype=torch.int32, device=x.device)
             ops.observer_minmax_msq(x2, mod, self.observer.state, self.observer_visual.state, self._seen)
+            # (the tensors behind these pointers live as long as the observers do)
+            self._fast_obs = (x2.shape[-1], ops.lib().mq_observer_minmax_msq, self.observer.state.data_ptr(),
+                              self.observer_visual.state.data_ptr(), self._seen.data_ptr(),
+                              self.observer.state, self.observer_visual.state, self._seen)
             return
         vis = mod.bool()
         if bool((~vis).any()):
@@ -885,17 +906,23 @@ def update_all_quantization_params(model, args=None):
         return len(slow)
     dev = next(o.state.device for q in fast for o in ([q.observer] + ([q.observer_visual] if q.msq else []))
                if o.state is not None)
-    rows = []
-    for q in fast:
-        zero2 = torch.zeros(2, dtype=torch.float32, device=dev)
-        t = q.observer.state if q.observer.state is not None else zero2
-        v = q.observer_visual.state if (q.msq and q.observer_visual.state is not None) else zero2
-        seen = getattr(q, "_seen", None)
-        if seen is None:  # (gather path / restored statistics: a state that exists has been seen)
-            seen = torch.tensor([float(q.observer.state is not None),
-                                 float(q.msq and q.observer_visual.state is not None)], device=dev)
-        rows.append(torch.cat([t.to(dev), v.to(dev), seen.to(dev, torch.float32)]))
-    host = torch.stack(rows).cpu()  # [n, 6] = {tmin, tmax, vmin, vmax, n_text, n_visual}: ONE copy
+    # three concatenations (not one per wrapper: 160 wrappers x a handful of tiny kernels is 10 ms)
+    zero2 = torch.zeros(2, dtype=torch.float32, device=dev)
+    t_states = [q.observer.state if q.observer.state is not None else zero2 for q in fast]
+    v_states = [q.observer_visual.state if (q.msq and q.observer_visual.state is not None) else zero2 for q in fast]
+    stats = torch.cat(t_states + v_states).cpu().view(2, len(fast), 2)  # ONE copy of all statistics
+    counted = [q for q in fast if getattr(q, "_seen", None) is not None]
+    counts = torch.cat([q._seen for q in counted]).cpu().view(-1, 2) if counted else None
+    host = torch.zeros(len(fast), 6)  # {tmin, tmax, vmin, vmax, n_text, n_visual}
+    host[:, 0:2], host[:, 2:4] = stats[0], stats[1]
+    ci = 0
+    for i, q in enumerate(fast):
+        if getattr(q, "_seen", None) is not None:
+            host[i, 4:6] = counts[ci].float()
+            ci += 1
+        else:  # (gather path / restored statistics: a state that exists has been seen)
+            host[i, 4] = float(q.observer.state is not None)
+            host[i, 5] = float(q.msq and q.observer_visual.state is not None)
     # the reference's expression, in the dtype of the statistics, for all observers at once
     by_dtype = {}
     for i, q in enumerate(fast):
@@ -919,6 +946,7 @@ def update_all_quantization_params(model, args=None):
         if not has_t and has_v:
             st = sv  # only visual tokens were ever seen
         host_pairs.append((st, sv if has_v else st, has_t or has_v, has_v and has_t))
+    zp0 = torch.zeros((), dtype=torch.int64, device=dev)
     for dt in by_dtype:
         idx = by_dtype[dt]
         pairs = torch.stack([torch.stack([host_pairs[i][0], host_pairs[i][1]]) for i in idx]).to(dev)  # [m, 2] in dt
@@ -930,7 +958,7 @@ def update_all_quantization_params(model, args=None):
                 continue
             qz = q.quantizer
             qz.scale = pairs[j, 0]
-            qz.zero_point = torch.zeros((), dtype=torch.int64, device=dev)
+            qz.zero_point = zp0
             has_v = bool(q.msq and host[i, 5] > 0)
             qz.scale_visual = pairs[j, 1] if has_v else None
             qz._dev_scales = f32[j]
