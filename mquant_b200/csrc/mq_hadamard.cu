@@ -359,6 +359,8 @@ static int hadamard_dispatch(const HadArgs& a, cudaStream_t st) {
         set_error("mq_hadamard: power-of-two n=%d outside [64, 8192]", a.n);
         return MQ_ERR_UNSUPPORTED;
     }
+  } else if (hadk_tc3_supported(a) && (rc = launch_hadk_tc3(a, st)) != MQ_ERR_UNSUPPORTED) {
+    // both Kronecker factors on tcgen05 (mq_hadamard_tc3.cu)
   } else if (hadk_tc2_supported(a) && (rc = launch_hadk_tc2(a, st)) != MQ_ERR_UNSUPPORTED) {
     // FWHT of the power-of-two factor in registers + hadK on tcgen05
   } else {

@@ -23,9 +23,13 @@ struct HadArgs {
 };
 
 
-// mq_hadamard_tc2.cu: power-of-two factor in registers, hadK factor on tcgen05 (default)
+// mq_hadamard_tc2.cu: power-of-two factor in registers, hadK factor on tcgen05 (n / had_k in {256, 512}; mq_debug_force_hadamard_kernel(2))
 bool hadk_tc2_supported(const HadArgs& a);
 int launch_hadk_tc2(const HadArgs& a, cudaStream_t st);
+
+// mq_hadamard_tc3.cu: n / had_k in {64, 128}: both factors on tcgen05, hadK as the A operand (default)
+bool hadk_tc3_supported(const HadArgs& a);
+int launch_hadk_tc3(const HadArgs& a, cudaStream_t st);
 
 // mq_hadamard_mma.cu: power-of-two n in {1024, 2048, 4096}: 16-point factors on mma.sync, warp per token
 bool fwht_mma_supported(const HadArgs& a);
