@@ -18,13 +18,32 @@ def main():
     ap.add_argument("--M", type=int, default=16384)
     ap.add_argument("--kernel", default="")
     ap.add_argument("--timeline", type=int, default=-1, help="MQ_HAD_DEBUG mask to run with bit 256 and dump stamps")
+    ap.add_argument("--timeline3", action="store_true", help="clock64 timeline of CTA 0 of hadk_tc3 (probes build)")
     a = ap.parse_args()
-    if a.kernel:
     hk_, K = hu.get_hadK(a.n)
     hk = hu.hadK_device(K, "cuda")
     x = (torch.randn(a.M, a.n, device="cuda") * 3).half()
     mod = (torch.rand(a.M, device="cuda") < 0.4).to(torch.uint8)
     scales = ops.make_scales(0.1134, 0.2871, "cuda")
+    if a.timeline3:
+        import ctypes
+        import numpy as np
+        from mquant_b200 import _lib
+        for _ in range(2):
+            ops.hadamard(x, had_k=K, hadk=hk, n=a.n, scales=scales, modality=mod, want_codes=True, want_f16=False)
+        torch.cuda.synchronize()
+        buf = np.zeros(96 * 16, dtype=np.int64)
+        fn = ctypes.CDLL(_lib.LIB_PATH).mq_debug_hadk_tc3_stamps if hasattr(_lib, "LIB_PATH") else _lib.lib().mq_debug_hadk_tc3_stamps
+        fn.argtypes = [ctypes.c_void_p]
+        assert fn(buf.ctypes.data) == 0
+        ts = buf.reshape(96, 16)
+        t0 = int(ts[0, 0])
+        names = ["tma0", "m1_xfull", "m1_d1emp", "m1_done", "m2_tfull", "m2_d2emp", "m2_done", "e2a_get", "e2a_done",
+                 "e2b_get", "e2b_done", "e1_temp", "e1_d1full", "e1_tile0", "e1_done"]
+        print("tok  " + " ".join(f"{n:>9s}" for n in names))
+        for u in list(range(0, 14)) + list(range(60, 72)):
+            print(f"{u:4d} " + " ".join(f"{int(ts[u, i]) - t0:9d}" for i in range(15)))
+        return
     if a.timeline >= 0:
         os.environ["MQ_HAD_DEBUG"] = str(a.timeline | 256)
         r = ops.hadamard(x, had_k=K, hadk=hk, n=a.n, scales=scales, modality=mod, want_codes=True, want_f16=False)
