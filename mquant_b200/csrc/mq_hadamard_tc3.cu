@@ -100,6 +100,39 @@ __device__ __forceinline__ uint32_t f16x2_rn(float lo, float hi) {
   return r;
 }
 
+// 32 fp32 accumulators of one output row -> fp16 (the second rounding point: hadK @ . -> fp16) ->
+// fp16 store and/or INT8 codes, 32 columns starting at `col` of the token's row
+template <bool NARROW>
+__device__ __forceinline__ void epi2_emit(const uint32_t (&v)[32], int8_t* qrow, __half* yrow, int col, const QScale& qs,
+                                          bool lane_ok, bool first, bool q32, bool y32, __half* x0_out, int64_t tok) {
+  uint32_t h[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) h[e] = f16x2_rn(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+  if (yrow != nullptr && lane_ok) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t w[8] = {h[8 * u], h[8 * u + 1], h[8 * u + 2], h[8 * u + 3], h[8 * u + 4], h[8 * u + 5], h[8 * u + 6], h[8 * u + 7]};
+      st_global_v8(yrow + col + u * 16, w, y32);
+    }
+  }
+  if (qrow != nullptr) {
+    uint32_t w[8];
+    const QNarrow qn = make_qnarrow(qs);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint4 hv = make_uint4(h[4 * u], h[4 * u + 1], h[4 * u + 2], h[4 * u + 3]);
+      const uint2 r = NARROW ? quant8_narrow(hv, qn) : quant8_bracket(hv, qs);
+      w[2 * u] = r.x;
+      w[2 * u + 1] = r.y;
+    }
+    if (first) {  // RMS split: channel 0 travels in fp16, its code is zero
+      if (lane_ok) x0_out[tok] = __ushort_as_half((unsigned short)(h[0] & 0xffffu));
+      w[0] &= 0xffffff00u;
+    }
+    if (lane_ok) st_global_v8(qrow + col, w, q32);
+  }
+}
+
 // The K loop of one MMA2 job.  The issuing thread shares its scheduler with three epilogue warps:
 // every instruction between two MMAs costs it an issue slot it has to win (measured: 117 clk per
 // MMA with the descriptors rebuilt per k-step, 240 clk while the second epilogue is busy), so the
@@ -205,7 +238,7 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       for (int lt = 0; lt < my_tokens; ++lt) {
         const int tok = (int)(blockIdx.x + (int64_t)lt * gridDim.x);
         for (int i = 0; i < c.tpt; ++i) {
-          mbar_wait(x_empty(xs), xph ^ 1u);
+          mbar_wait_sleep(x_empty(xs), xph ^ 1u);
           mbar_arrive_expect_tx(x_full(xs), (uint32_t)c.x_bytes);
 #pragma unroll
           for (int sub = 0; sub < NS; ++sub)
@@ -224,9 +257,9 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
     const int total_tiles = my_tokens * c.tpt;
     int ti = 0, lt1 = 0;  // (tile of the token, token: for the probes only)
     for (int g = 0; g < total_tiles; ++g) {
-      mbar_wait(x_full(xs), xph);
+      mbar_wait_sleep(x_full(xs), xph);
       if (ti == 0) stamp(lt1, 1);
-      mbar_wait(d1_empty(d1), d1ph ^ 1u);
+      mbar_wait_sleep(d1_empty(d1), d1ph ^ 1u);
       if (ti == 0) stamp(lt1, 2);
       tc_fence_after();
       if (elect_one()) {
@@ -255,14 +288,14 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
     const int nks = c.Kpad / 16;
     int tg = 0, d2 = 0;
     uint32_t tph = 0, d2ph = 0;
-    mbar_wait(a2_ready, 0);
+    mbar_wait_sleep(a2_ready, 0);
     for (int g = 0; g < my_groups; ++g) {
       const int tig = min(G, my_tokens - g * G);  // tokens in this group
       const uint32_t idesc = idesc0 | ((uint32_t)((P * tig) >> 3) << 17);
-      mbar_wait(t_full(tg), tph);
+      mbar_wait_sleep(t_full(tg), tph);
       stamp(g * G, 4);
       for (int mt = 0; mt < c.mt; ++mt) {
-        mbar_wait(d2_empty(d2), d2ph ^ 1u);
+        mbar_wait_sleep(d2_empty(d2), d2ph ^ 1u);
         if (mt == 0) stamp(g * G, 5);
         tc_fence_after();
         if (elect_one()) {
@@ -270,6 +303,7 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
           const uint32_t tbase = sT + tg * (G * c.t_bytes);
           const uint32_t tm = tmem_base + (uint32_t)(D2_COL0 + d2 * 128);
           const uint64_t ad = make_sw128_desc(arow, 0, 1024), bd = make_sw128_desc(tbase, lbo, 1024);
+          if (G == 2) stamp(g * G + 1, 4 + 2 * mt);  // (probes, odd rows: issue of job A / B starts, ends)
           switch (nks) {  // (the common hadK sizes 108 / 140 / 156 / 172 fully unrolled)
             case 7: issue_mma2<7>(tm, ad, bd, idesc); break;
             case 9: issue_mma2<9>(tm, ad, bd, idesc); break;
@@ -277,6 +311,7 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
             case 11: issue_mma2<11>(tm, ad, bd, idesc); break;
             default: issue_mma2<0>(tm, ad, bd, idesc, nks); break;
           }
+          if (G == 2) stamp(g * G + 1, 5 + 2 * mt);
           umma_commit(d2_full(d2));
           if (mt == c.mt - 1) umma_commit(t_empty(tg));
         }
@@ -289,36 +324,57 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
   } else if (warp < EPI2_WARP0 + 8) {
     // ===================== second epilogue: D2 -> fp16 -> fp16 store / INT8 codes -> HBM ==========
     // First: hadK as [k' rows][k] K-major SWIZZLE_128B, zero padded to Kpad x (kb2*64), k-block kb
-    // at kb * Kpad * 128.  Rows are only 8-byte aligned (had_k = 4 mod 8 for most sizes): 64-bit
-    // loads, four chunks in flight per thread.
+    // at kb * Kpad * 128.  The matrix is read as a flat array of 16-byte words, all loads of a
+    // thread in flight together (one word at a time from its rows took 25 k cycles with every CTA
+    // of the grid missing in L2 at once); a word is two 4-element halves, each inside one row
+    // whenever had_k % 4 == 0.  The padding (columns / rows >= had_k) is zeroed separately.
     {
-      const int nchunk = c.Kpad * c.kb2 * 8, cpr = c.kb2 * 8;
-      const bool vec = (c.had_k & 3) == 0 && (reinterpret_cast<uintptr_t>(a.hadk) & 7u) == 0;
-      for (int id0 = threadIdx.x - EPI2_WARP0 * 32; id0 < nchunk; id0 += 4 * 256) {
-        uint32_t w[4][4];
-        uint32_t dst[4];
+      const int tid = threadIdx.x - EPI2_WARP0 * 32;
+      auto sdst = [&](int row, int k) {
+        return sA2 + (uint32_t)(k >> 6) * (uint32_t)(c.Kpad * 128) + (uint32_t)row * 128u +
+               ((uint32_t)(((k & 63) >> 3) ^ (row & 7)) << 4) + (uint32_t)(k & 7) * 2u;
+      };
+      const int kcols = c.kb2 * 64;
+      if ((c.had_k & 3) == 0 && (reinterpret_cast<uintptr_t>(a.hadk) & 15u) == 0) {
+        const int nhalf = c.had_k * c.had_k / 4, nword = (nhalf + 1) / 2;
+        const uint4* src = reinterpret_cast<const uint4*>(a.hadk);
+        for (int w0 = tid; w0 < nword; w0 += 8 * 256) {
+          uint4 v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int id = id0 + u * 256;
-          const int row = id / cpr, rem = id - row * cpr, kb = rem >> 3, ch = rem & 7;
-          const int k0 = kb * 64 + ch * 8;
-          w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u;
-          dst[u] = sA2 + kb * (c.Kpad * 128) + row * 128 + ((uint32_t)(ch ^ (row & 7)) << 4);
-          if (id < nchunk && row < c.had_k && k0 < c.had_k) {
-            const __half* src = a.hadk + row * c.had_k + k0;
-            if (vec && k0 + 8 <= c.had_k) {
-              const uint2 lo = __ldg(reinterpret_cast<const uint2*>(src)), hi = __ldg(reinterpret_cast<const uint2*>(src) + 1);
-              w[u][0] = lo.x; w[u][1] = lo.y; w[u][2] = hi.x; w[u][3] = hi.y;
-            } else {
+          for (int u = 0; u < 8; ++u) {
+            const int w = w0 + u * 256;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (2 * w + 1 < nhalf) v[u] = __ldg(src + w);
+            else if (2 * w < nhalf) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(src + w)); v[u].x = t.x; v[u].y = t.y; }
+          }
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (k0 + e < c.had_k) w[u][e >> 1] |= (uint32_t)__half_as_ushort(__ldg(src + e)) << (16 * (e & 1));
+          for (int u = 0; u < 8; ++u) {
+            const int w = w0 + u * 256;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const int e = (2 * w + hf) * 4;  // flat element index of this half
+              if (e < c.had_k * c.had_k) {
+                const int row = e / c.had_k, k = e - row * c.had_k;
+                asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sdst(row, k)), "r"(hf ? v[u].z : v[u].x), "r"(hf ? v[u].w : v[u].y) : "memory");
+              }
             }
           }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (id0 + u * 256 < nchunk) st_shared_v4(dst[u], w[u][0], w[u][1], w[u][2], w[u][3]);
+      } else {
+        for (int e = tid; e < c.had_k * c.had_k; e += 256) {
+          const int row = e / c.had_k, k = e - row * c.had_k;
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(sdst(row, k)), "h"(__half_as_ushort(__ldg(a.hadk + e))) : "memory");
+        }
+      }
+      // zero padding: columns had_k .. kcols-1 of the rows < had_k, whole rows had_k .. Kpad-1
+      const int padc = kcols - c.had_k;
+      for (int id = tid; id < c.had_k * padc; id += 256) {
+        const int row = id / padc, k = c.had_k + (id - row * padc);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(sdst(row, k)), "h"((unsigned short)0) : "memory");
+      }
+      for (int id = tid; id < (c.Kpad - c.had_k) * (kcols / 8); id += 256) {
+        const int row = c.had_k + id / (kcols / 8), k = (id % (kcols / 8)) * 8;
+        st_shared_v4(sdst(row, k), 0u, 0u, 0u, 0u);
       }
       fence_async_smem();
       __syncwarp();
@@ -357,7 +413,7 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
         const int kp = mt == 0 ? l : (c.Kpad - 128 + l);
         const bool lane_ok = have && (mt == 0 ? true : (l >= lane0_mt1)) && kp < c.had_k;
         const bool warp_ok = have && (mt == 0 ? (quad * 32 < c.had_k) : (quad * 32 + 31 >= lane0_mt1 && c.Kpad - 128 + quad * 32 < c.had_k));
-        mbar_wait(d2_full(d2), d2ph);
+        mbar_wait_sleep(d2_full(d2), d2ph);
         if (warp == EPI2_WARP0 && mt == 0) stamp(lt, 7);
         if (warp == EPI2_WARP0 + 3 && mt == c.mt - 1) stamp(lt, 9);
         tc_fence_after();
@@ -370,36 +426,16 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
           tmem_ld32_nowait(taddr + cc0 * 32, va);
           tmem_ld32_nowait(taddr + (cc0 + cstep) * 32, vb);
           tmem_wait_ld();
-#pragma unroll
-          for (int ci = 0; ci < 2; ++ci) {
-            uint32_t(&cur)[32] = ci ? vb : va;
-            const int col = (G == 2 ? ci : (cc0 + ci * cstep)) * 32;  // column of the token
-            uint32_t h[16];  // second rounding point (hadK @ . -> fp16)
-#pragma unroll
-            for (int e = 0; e < 16; ++e) h[e] = f16x2_rn(__uint_as_float(cur[2 * e]), __uint_as_float(cur[2 * e + 1]));
-            if (lane_ok) {
-              if (want_y) {
-#pragma unroll
-                for (int v = 0; v < 2; ++v) {
-                  const uint32_t w[8] = {h[8 * v], h[8 * v + 1], h[8 * v + 2], h[8 * v + 3], h[8 * v + 4], h[8 * v + 5], h[8 * v + 6], h[8 * v + 7]};
-                  st_global_v8(yrow + col + v * 16, w, y32);
-                }
-              }
-              if (want_q) {
-                uint32_t w[8];
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                  const uint2 r = quant8(make_uint4(h[4 * v], h[4 * v + 1], h[4 * v + 2], h[4 * v + 3]), qs);
-                  w[2 * v] = r.x;
-                  w[2 * v + 1] = r.y;
-                }
-                if (split && col == 0 && kp == 0) {
-                  a.x0_out[tok] = __ushort_as_half((unsigned short)(h[0] & 0xffffu));
-                  w[0] &= 0xffffff00u;
-                }
-                st_global_v8(qrow + col, w, q32);
-              }
-            }
+          const int col0 = (G == 2 ? 0 : cc0) * 32, col1 = (G == 2 ? 1 : cc0 + cstep) * 32;  // columns of the token
+          const bool first = split && col0 == 0 && kp == 0;
+          // (the test for the division-free quantiser is hoisted: inside quant8 it would cut the 64
+          // independent elements of a thread into basic blocks of 8 -- measured IPC 0.19 per warp)
+          if (qs.narrow) {
+            epi2_emit<true>(va, qrow, yrow, col0, qs, lane_ok, first, q32, y32, a.x0_out, tok);
+            epi2_emit<true>(vb, qrow, yrow, col1, qs, lane_ok, false, q32, y32, a.x0_out, tok);
+          } else {
+            epi2_emit<false>(va, qrow, yrow, col0, qs, lane_ok, first, q32, y32, a.x0_out, tok);
+            epi2_emit<false>(vb, qrow, yrow, col1, qs, lane_ok, false, q32, y32, a.x0_out, tok);
           }
         }
         tc_fence_before();
@@ -421,9 +457,9 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       const uint32_t tbuf = sT + (uint32_t)(tg * G + tin) * (uint32_t)c.t_bytes;
       for (int i = 0; i < c.tpt; ++i) {
         const int rows_here = min(c.xrows, c.Kpad - i * c.xrows);
-        if (i == 0 && tin == 0) mbar_wait(t_empty(tg), tph ^ 1u);
+        if (i == 0 && tin == 0) mbar_wait_sleep(t_empty(tg), tph ^ 1u);
         if (warp == EPI1_WARP0 && i == 0) stamp(lt, 11);
-        mbar_wait(d1_full(d1), d1ph);
+        mbar_wait_sleep(d1_full(d1), d1ph);
         if (warp == EPI1_WARP0 && i == 0) stamp(lt, 12);
         tc_fence_after();
         if (quad * 32 < rows_here) {

@@ -30,21 +30,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-// Same, for waits that normally last long (a consumer waiting for work): the thread is suspended
-// by the hardware (time-limit hint 20 us) per probe instead of re-issuing the test -- spinning warps
-// were 17 % of all issued instructions in the Hadamard kernel and compete with the working
-// warps of their scheduler
-__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity) {
+// Same, for warps that share a scheduler with working warps: a failed probe backs off with
+// nanosleep instead of re-issuing immediately.  (Spinning issuer / consumer warps competed with
+// the one epilogue warp their own barrier was waiting for: it finished 1700-2000 cycles late.
+// A time-limit hint on try_wait instead made wake-ups slower, 10-20 % on the whole kernel.)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   uint32_t done;
-  do {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  while (!done) {
+    __nanosleep(32);
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)
+        : "r"(bar), "r"(parity)
         : "memory");
-  } while (!done);
+  }
 }
 // One lane of a converged warp, chosen by the hardware.  Unlike `lane == 0` the compiler knows that
 // exactly one thread executes the guarded code: tcgen05 / TMA instructions (uniform-datapath

@@ -42,7 +42,7 @@ def main():
                  "e2b_get", "e2b_done", "e1_temp", "e1_d1full", "e1_tile0", "e1_done"]
         print("tok  " + " ".join(f"{n:>9s}" for n in names))
         for u in list(range(0, 14)) + list(range(60, 72)):
-            print(f"{u:4d} " + " ".join(f"{int(ts[u, i]) - t0:9d}" for i in range(15)))
+            print(f"{u:4d} " + " ".join(f"{int(ts[u, i]) - t0:9d}" for i in range(16)))
         return
     if a.timeline >= 0:
         os.environ["MQ_HAD_DEBUG"] = str(a.timeline | 256)
