@@ -34,7 +34,7 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, probes: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, probes: bool = False, stamps: bool = False) -> str:
     """probes=True defines MQ_PROBES: the bottleneck probes of tools/gemm_probe.py / had_probe.py
     (MQ_GEMM_DEBUG / MQ_HAD_DEBUG masks) are compiled in -- never for a shipped library."""
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
@@ -46,8 +46,8 @@ def build(force: bool = False, verbose: bool = False, probes: bool = False) -> s
     for s in srcs:
         o = os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        if force or probes or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-DMQ_PROBES"] if probes else []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        if force or probes or stamps or _stale(o, [s] + hdrs):
+            cmd = [nvcc] + NVCC_FLAGS + (["-DMQ_PROBES"] if probes else []) + (["-DMQ_STAMPS"] if stamps else []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):
@@ -71,4 +71,4 @@ def build(force: bool = False, verbose: bool = False, probes: bool = False) -> s
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, probes="--probes" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, probes="--probes" in sys.argv, stamps="--stamps" in sys.argv))

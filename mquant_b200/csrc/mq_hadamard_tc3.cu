@@ -36,6 +36,8 @@
 // HBM traffic per token: 2*n_in read + n (codes) [+ 2*n fp16].
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "mq_common.cuh"
 #include "mq_hadamard_args.cuh"
 #include "mq_tc.cuh"
@@ -51,8 +53,6 @@ constexpr int NUM_THREADS = 512;
 // epilogue of the previous job was running on the same scheduler.)
 constexpr int EPI2_WARP0 = 0, EPI1_WARP0 = 8, W_TMA = 12, W_MMA1 = 13, W_MMA2 = 14;
 constexpr int TMEM_COLS = 512;
-constexpr int D2_COL0 = 256;
-constexpr int D2N = 2;  // D2 jobs in TMEM, 128 columns each
 constexpr int MAX_XS = 8, MAX_TG = 4;
 
 struct Cfg {
@@ -70,8 +70,9 @@ struct Params {
   Cfg c;
 };
 
-#ifdef MQ_PROBES
-// clock64 timeline of CTA 0 (tools/had_probe.py --timeline3): 16 slots per token, first 96 tokens
+#ifdef MQ_STAMPS
+// clock64 timeline of CTA 0 (tools/had_probe.py --timeline3, build.py --stamps; the stamps themselves
+// slow the kernel by a third: read the order of events, not the durations): 16 slots per token, first 96 tokens
 __device__ long long g_stamps[96 * 16];
 __device__ __forceinline__ void stamp(int lt, int slot) {
   if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && lt < 96) g_stamps[lt * 16 + slot] = clock64();
@@ -156,13 +157,17 @@ __device__ __forceinline__ void issue_mma2(uint32_t tm, uint64_t ad, uint64_t bd
   }
 }
 
-// NS = P / 64 sub-blocks per row; G = 2 / NS tokens per MMA2 job (N = 128 columns)
-template <int NS>
+// NS = P / 64 sub-blocks per row; G = 2 / NS tokens per MMA2 job (N = 128 columns); D1N = D1 tiles in TMEM
+template <int NS, int D1N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
   constexpr int P = 64 * NS;
   constexpr int G = 2 / NS;
-  constexpr int D1N = 4 / NS;  // D1 tiles in TMEM (P columns each)
+  // TMEM: D1 tiles (P columns each) first, then the D2 jobs (128 columns each).  The first epilogue
+  // is never behind (two D1 tiles suffice); the MMA2 <-> second-epilogue hand-over is the
+  // latency-critical loop, so it gets the third slot where the columns allow (P = 64).
+  constexpr int D2_COL0 = D1N * P;
+  constexpr int D2N = (TMEM_COLS - D2_COL0) / 128;
   const HadArgs& a = prm.a;
   const Cfg& c = prm.c;
   extern __shared__ uint8_t smem_raw[];
@@ -171,7 +176,7 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t sA2 = base + c.a2_off, sH = base + c.h_off, sX = base + c.x_off, sT = base + c.t_off;
   const uint32_t bar0 = base + c.bar_off;
-  // barrier map: x_full[8] x_empty[8] d1_full[4] d1_empty[4] t_full[4] t_empty[4] d2_full[2] d2_empty[2] a2_ready
+  // barrier map: x_full[8] x_empty[8] d1_full[4] d1_empty[4] t_full[4] t_empty[4] d2_full[4] d2_empty[4] a2_ready
   auto x_full = [&](int s) { return bar0 + 8u * s; };
   auto x_empty = [&](int s) { return bar0 + 8u * (MAX_XS + s); };
   auto d1_full = [&](int s) { return bar0 + 8u * (2 * MAX_XS + s); };
@@ -179,9 +184,9 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
   auto t_full = [&](int s) { return bar0 + 8u * (2 * MAX_XS + 8 + s); };
   auto t_empty = [&](int s) { return bar0 + 8u * (2 * MAX_XS + 8 + MAX_TG + s); };
   auto d2_full = [&](int s) { return bar0 + 8u * (2 * MAX_XS + 8 + 2 * MAX_TG + s); };
-  auto d2_empty = [&](int s) { return bar0 + 8u * (2 * MAX_XS + 10 + 2 * MAX_TG + s); };
-  const uint32_t a2_ready = bar0 + 8u * (2 * MAX_XS + 12 + 2 * MAX_TG);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + c.bar_off + 8 * (2 * MAX_XS + 13 + 2 * MAX_TG));
+  auto d2_empty = [&](int s) { return bar0 + 8u * (2 * MAX_XS + 12 + 2 * MAX_TG + s); };
+  const uint32_t a2_ready = bar0 + 8u * (2 * MAX_XS + 16 + 2 * MAX_TG);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + c.bar_off + 8 * (2 * MAX_XS + 17 + 2 * MAX_TG));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -199,7 +204,7 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       mbar_init(d1_full(s), 1);
       mbar_init(d1_empty(s), 4);  // the four first-epilogue warps
     }
-    for (int s = 0; s < D2N; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(d2_full(s), 1);
       mbar_init(d2_empty(s), 8);  // the eight second-epilogue warps
     }
@@ -299,7 +304,12 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
         if (mt == 0) stamp(g * G, 5);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t arow = sA2 + (uint32_t)(mt == 0 ? 0 : (c.Kpad - 128)) * 128u;
+          // second M-tile: rows Kpad-128 .. Kpad-1 (new rows in the LAST lanes) for even groups, rows
+          // 128 .. 255 (new rows in the FIRST lanes; what it reads past hadK is finite garbage or
+          // somebody's data, and only feeds rows nobody reads) for odd groups: the second epilogue of
+          // this job then alternates between the TMEM lane quadrants 2-3 and 0-1, whose warps would
+          // otherwise carry two jobs per group against one
+          const uint32_t arow = sA2 + (uint32_t)(mt == 0 ? 0 : ((g & 1) ? 128 : c.Kpad - 128)) * 128u;
           const uint32_t tbase = sT + tg * (G * c.t_bytes);
           const uint32_t tm = tmem_base + (uint32_t)(D2_COL0 + d2 * 128);
           const uint64_t ad = make_sw128_desc(arow, 0, 1024), bd = make_sw128_desc(tbase, lbo, 1024);
@@ -410,9 +420,12 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       qs.narrow = vis ? q_vis.narrow : q_text.narrow;
       if (have && want_q && l == 0 && (G == 2 || set == 0) && a.srow_out != nullptr) a.srow_out[tok] = qs.s;
       for (int mt = 0; mt < c.mt; ++mt) {
-        const int kp = mt == 0 ? l : (c.Kpad - 128 + l);
-        const bool lane_ok = have && (mt == 0 ? true : (l >= lane0_mt1)) && kp < c.had_k;
-        const bool warp_ok = have && (mt == 0 ? (quad * 32 < c.had_k) : (quad * 32 + 31 >= lane0_mt1 && c.Kpad - 128 + quad * 32 < c.had_k));
+        const bool alt = (g & 1) != 0;  // (see the MMA2 issuer)
+        const int kp = mt == 0 ? l : alt ? 128 + l : (c.Kpad - 128 + l);
+        const bool lane_ok = have && (mt == 0 || alt || l >= lane0_mt1) && kp < c.had_k;
+        const bool warp_ok = have && (mt == 0   ? (quad * 32 < c.had_k)
+                                      : alt     ? (128 + quad * 32 < c.had_k)
+                                                : (quad * 32 + 31 >= lane0_mt1 && c.Kpad - 128 + quad * 32 < c.had_k));
         mbar_wait_sleep(d2_full(d2), d2ph);
         if (warp == EPI2_WARP0 && mt == 0) stamp(lt, 7);
         if (warp == EPI2_WARP0 + 3 && mt == c.mt - 1) stamp(lt, 9);
@@ -442,6 +455,7 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
         __syncwarp();
         if (warp == EPI2_WARP0 && mt == 0) stamp(lt, 8);
         if (warp == EPI2_WARP0 + 3 && mt == c.mt - 1) stamp(lt, 10);
+        if (G == 2 && mt == 1 && quad >= 2) stamp(g * G + 1, warp == 2 ? 8 : warp == 3 ? 9 : warp == 6 ? 10 : 15);  // (probes: job B done)
         if (lane == 0) mbar_arrive(d2_empty(d2));
         if (++d2 == D2N) { d2 = 0; d2ph ^= 1u; }
       }
@@ -562,7 +576,7 @@ static int launch(const HadArgs& a, cudaStream_t st) {
   c.t_bytes = NS * c.Kpad * 128;
   const int a2 = round_up(c.kb2 * c.Kpad * 128, 1024);
   const int hb = 64 * 128;
-  const int bars = 8 * (2 * MAX_XS + 13 + 2 * MAX_TG) + 16;
+  const int bars = 8 * (2 * MAX_XS + 17 + 2 * MAX_TG) + 16;
   const int budget = 227 * 1024 - 1024 - round_up(bars, 128);
   // X tiles: the token's Kpad rows in equal parts of at most 128 rows (a multiple of 16: whole
   // k-steps of MMA2 and whole swizzle atoms).  MMA1 always reads 128 rows; what lies past a short
@@ -602,15 +616,22 @@ static int launch(const HadArgs& a, cudaStream_t st) {
     return MQ_ERR_CUDA;
   }
   const int smem = c.total + 1024;
-  MQ_DYN_SMEM(hadk_tc3_kernel<NS>, smem);
   const int grid = (int)(a.M < num_sms() ? a.M : num_sms());
-  hadk_tc3_kernel<NS><<<grid, NUM_THREADS, smem, st>>>(tmap, prm);
+#ifdef MQ_PROBES
+  if (NS == 1 && getenv("MQ_HAD_D1N4") != nullptr) {  // (experiment: four D1 tiles + two D2 jobs)
+    MQ_DYN_SMEM((hadk_tc3_kernel<NS, 4 / NS>), smem);
+    hadk_tc3_kernel<NS, 4 / NS><<<grid, NUM_THREADS, smem, st>>>(tmap, prm);
+    return MQ_OK;
+  }
+#endif
+  MQ_DYN_SMEM((hadk_tc3_kernel<NS, 2>), smem);
+  hadk_tc3_kernel<NS, 2><<<grid, NUM_THREADS, smem, st>>>(tmap, prm);
   return MQ_OK;
 }
 
 }  // namespace hadtc3
 
-#ifdef MQ_PROBES
+#ifdef MQ_STAMPS
 extern "C" int mq_debug_hadk_tc3_stamps(long long* dst_host) {
   return cudaMemcpyFromSymbol(dst_host, hadtc3::g_stamps, sizeof(long long) * 96 * 16) == cudaSuccess ? 0 : -3;
 }

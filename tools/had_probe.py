@@ -24,7 +24,8 @@ def main():
     hk = hu.hadK_device(K, "cuda")
     x = (torch.randn(a.M, a.n, device="cuda") * 3).half()
     mod = (torch.rand(a.M, device="cuda") < 0.4).to(torch.uint8)
-    scales = ops.make_scales(0.1134, 0.2871, "cuda")
+    # calibrated-looking scales: fp16 VALUES (MinmaxObserver), the division-free quantiser path
+    scales = ops.make_scales(float(torch.tensor(0.1134, dtype=torch.float16)), float(torch.tensor(0.2871, dtype=torch.float16)), "cuda")
     if a.timeline3:
         import ctypes
         import numpy as np
