@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmquant_b200.so")
+# (MQUANT_B200_LIB: an experimental build of the same library, tools/ A/B runs only)
+LIB_PATH = os.environ.get("MQUANT_B200_LIB") or os.path.join(_HERE, "libmquant_b200.so")
 
 MQ_FLAG_SPLIT = 1
 MQ_FLAG_FP32_HAD = 2

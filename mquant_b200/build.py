@@ -34,20 +34,25 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, probes: bool = False, stamps: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, probes: bool = False, stamps: bool = False,
+          defines: tuple = (), out: str | None = None) -> str:
     """probes=True defines MQ_PROBES: the bottleneck probes of tools/gemm_probe.py / had_probe.py
     (MQ_GEMM_DEBUG / MQ_HAD_DEBUG masks) are compiled in -- never for a shipped library."""
+    # (defines / out: an experimental variant next to the product library, for same-box A/B runs with
+    # MQUANT_B200_LIB=<out>; objects go to their own directory)
+    lib = out or LIB
+    obj_dir = OBJ_DIR if out is None else OBJ_DIR + "_" + os.path.basename(out).replace(".", "_")
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(os.path.dirname(HERE), "include", "mquant_b200.h")]
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     jobs = []
     objs = []
     for s in srcs:
-        o = os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + ".o")
+        o = os.path.join(obj_dir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
         if force or probes or stamps or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-DMQ_PROBES"] if probes else []) + (["-DMQ_STAMPS"] if stamps else []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + (["-DMQ_PROBES"] if probes else []) + (["-DMQ_STAMPS"] if stamps else []) + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):
@@ -61,14 +66,17 @@ def build(force: bool = False, verbose: bool = False, probes: bool = False, stam
                     sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
                 if r.returncode != 0:
                     raise RuntimeError("nvcc failed for " + cmd[-3])
-    if jobs or force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    if jobs or force or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link of libmquant_b200.so failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, probes="--probes" in sys.argv, stamps="--stamps" in sys.argv))
+    _defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    _out = next((a[6:] for a in sys.argv[1:] if a.startswith("--out=")), None)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, probes="--probes" in sys.argv, stamps="--stamps" in sys.argv,
+                defines=_defs, out=_out))

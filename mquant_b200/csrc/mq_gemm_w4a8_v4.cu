@@ -22,6 +22,14 @@
 
 #include "mq_gemm_common.cuh"
 
+// Waits that normally last long (the epilogue waiting for a whole tile, the producers waiting for
+// a ring slot): with MQ_GEMM_SLEEPWAIT a failed probe backs off instead of re-issuing at once
+#ifdef MQ_GEMM_SLEEPWAIT
+#define MQ_WAIT_LONG(bar, par) mbar_wait_sleep(bar, par)
+#else
+#define MQ_WAIT_LONG(bar, par) mbar_wait(bar, par)
+#endif
+
 namespace mq {
 namespace gemm {
 namespace v4 {
@@ -135,7 +143,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int t = unit; t < total_tiles; t += num_units) {
         const int mb = t / p.n_tiles;
         for (int kb = 0; kb < p.k_tiles; ++kb) {
-          mbar_wait(aempty_bar(stage), phase ^ 1u);
+          MQ_WAIT_LONG(aempty_bar(stage), phase ^ 1u);
           if (MQ_PROBE(p, 2u)) {
             mbar_arrive(afull_bar(stage));
           } else {
@@ -155,7 +163,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int t = unit; t < total_tiles; t += num_units) {
         const int nb = t % p.n_tiles;
         for (int kb = 0; kb < p.k_tiles; ++kb) {
-          mbar_wait(wempty_bar(ws), wphase ^ 1u);
+          MQ_WAIT_LONG(wempty_bar(ws), wphase ^ 1u);
           mbar_arrive_expect_tx(wfull_bar(ws), W_STAGE);
           bulk_load(sW + ws * W_STAGE, p.w4 + w4_blob_offset(nb, kb, p.k_tiles), W_STAGE, wfull_bar(ws));
           if (++ws == WSTAGES) { ws = 0; wphase ^= 1u; }
@@ -335,7 +343,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int h = 0; h < 2; ++h) {
         const int m_warp0 = mb * BM + h * BMH + quad * 32;
         const float sa = h ? sa2[1] : sa2[0], x0v = h ? x0v2[1] : x0v2[0];
-        mbar_wait(tfull_bar(h), tile_phase);
+        MQ_WAIT_LONG(tfull_bar(h), tile_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * BN + col0);
         uint32_t va[32], vb[32];

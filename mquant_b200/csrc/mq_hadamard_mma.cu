@@ -112,9 +112,11 @@ struct Traits {
   static_assert(FOLD >= 4 + FB, "scale folding");
 };
 
-// MODE: bit 0 = codes, bit 1 = fp16 output
-template <int NB, int FB, int MODE>
-__global__ void __launch_bounds__(WARPS * 32, Traits<NB, FB>::MIN_CTAS) fwht_mma_kernel(const HadArgs a) {
+// MODE: bit 0 = codes, bit 1 = fp16 output.  NARROW: both scales take the division-free quantiser
+// (decided once per kernel: a test per group of 4 codes cuts the epilogue into basic blocks of 4
+// elements and serialises it)
+template <int NB, int FB, int MODE, bool NARROW>
+__device__ __forceinline__ void fwht_mma_body(const HadArgs& a) {
   using T = Traits<NB, FB>;
   constexpr int N = T::N, CH = T::CH, BL = T::BL, NBUF = T::NBUF;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(WARPS * 32, Traits<NB, FB>::MIN_CTAS) fwht_mma
           const int col = b * 256 + 128 * tl;  // + group and word offsets, already in qrow / yrow
           if (want_y) *reinterpret_cast<uint2*>(yrow + col) = make_uint2(ha, hb);
           if (want_q) {
-            const uint32_t codes0 = qs.narrow ? quant4_narrow(ha, hb, qs.n) : quant4_exact(ha, hb, qs.s);  // (division: rare scales only)
+            const uint32_t codes0 = NARROW ? quant4_narrow(ha, hb, qs.n) : quant4_exact(ha, hb, qs.s);  // (division: rare scales only)
             uint32_t codes = codes0;
             if (b == 0 && tl == 0 && split && ch == 0 && lane == 0) {
               a.x0_out[m] = __ushort_as_half((unsigned short)(ha & 0xffffu));
@@ -305,6 +307,19 @@ __global__ void __launch_bounds__(WARPS * 32, Traits<NB, FB>::MIN_CTAS) fwht_mma
       if (want_y) yrow += BL * 256;
     }
   }
+}
+
+template <int NB, int FB, int MODE>
+__global__ void __launch_bounds__(WARPS * 32, Traits<NB, FB>::MIN_CTAS) fwht_mma_kernel(const HadArgs a) {
+  bool narrow = true;
+  if (MODE & 1) {
+    const float s0 = __ldg(a.scales), s1 = __ldg(a.scales + 1);
+    narrow = ((__float_as_uint(s0) | __float_as_uint(s1)) & 0x1fffu) == 0u;  // (make_qscale's test)
+  }
+  if (narrow)
+    fwht_mma_body<NB, FB, MODE, true>(a);
+  else
+    fwht_mma_body<NB, FB, MODE, false>(a);
 }
 
 template <int NB, int FB, int MODE>
