@@ -31,6 +31,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "mq_common.cuh"
 #include "mq_hadamard_args.cuh"
@@ -39,6 +40,9 @@
 namespace mq {
 namespace hadtc2 {
 using namespace mq::tc;
+#ifdef MQ_TC2_SLEEP
+#define mbar_wait mbar_wait_sleep
+#endif
 
 constexpr int NUM_THREADS = 512;  // 4 warps per scheduler -> 128 registers per thread (the transform keeps 64 fp32 live)
 constexpr int XF_WARP0 = 2, NUM_XF_WARPS = 6;
@@ -299,7 +303,11 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
         // Two 16-column chunks (this warp's ch and ch + 2) are converted together: four
         // independent quantiser streams give the scheduler the ILP that two epilogue warps per
         // SM sub-partition cannot (the epilogue is latency bound, not issue bound).
-        auto process2 = [&](const uint32_t (&v0)[16], int ch0, const uint32_t (&v1)[16], bool two) {
+        // (NARROW: the division-free quantiser, chosen once per unit -- a test inside quant8 would cut
+        // the independent elements of a thread into basic blocks of 8)
+        auto process2 = [&](auto narrow_tag, const uint32_t (&v0)[16], int ch0, const uint32_t (&v1)[16], bool two) {
+          constexpr bool NARROW = decltype(narrow_tag)::value;
+          const QNarrow qn = make_qnarrow(qs);
           if (MQ_HPROBE(prm, 2u)) return;  // probe: TMEM loads only
           uint32_t w[8];
 #pragma unroll
@@ -318,7 +326,7 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
               }
             }
             uint2 r = make_uint2(0u, 0u);
-            if (want_q) r = quant8(h, qs);
+            if (want_q) r = NARROW ? quant8_narrow(h, qn) : quant8_bracket(h, qs);
             if (split && ch == 0 && g == 0 && j == 0) {
               if (live) a.x0_out[tok] = reinterpret_cast<const __half*>(&h)[0];
               r.x &= 0xffffff00u;
@@ -346,7 +354,10 @@ hadk_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
           tmem_ld16_nowait(taddr + ch * 16, va);
           if (two) tmem_ld16_nowait(taddr + (ch + 2) * 16, vb);
           tmem_wait_ld();
-          process2(va, ch, vb, two);
+          if (qs.narrow)
+            process2(std::true_type{}, va, ch, vb, two);
+          else
+            process2(std::false_type{}, va, ch, vb, two);
         }
       }
       tc_fence_before();
