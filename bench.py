@@ -431,12 +431,15 @@ def main():
     pk = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
     bf16_burst = float(pk.get("bf16_tflops", 1590.0))
     bf16_sus = float(pk.get("bf16_tflops_sustained", 1400.0))
-    if int8_sustained:
-        # the GEMM is timed inside a long step (power-capped clocks): sustained library figure
-        peak, peak_src = int8_sustained, ("cuBLASLt INT8 torch._int_mm 8192^3, back to back ~1.5 s, measured in this run "
-                                          "(MEASURED_PEAKS.json has no INT8 entry)")
-    else:
-        peak, peak_src = 2.0 * bf16_sus, "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (no INT8 library GEMM available)"
+    # `peak` must be a ceiling: the highest dense-INT8 rate measured on this pool, i.e. the larger of
+    # 2 x the driver-measured bf16 burst (INT8 issues at twice the bf16 rate) and the best cuBLASLt
+    # INT8 launch of this run.  (Round 1 divided by the sustained library figure, which this kernel
+    # exceeds.)  The sustained / nominal denominators stay alongside.
+    cands = [(2.0 * bf16_burst, "2 x bf16_tflops (burst) of MEASURED_PEAKS.json")]
+    if int8_burst:
+        cands.append((int8_burst, "cuBLASLt INT8 torch._int_mm 8192^3, best launch of this run"))
+    peak, peak_src = max(cands)
+    peak_src = "highest measured dense INT8-equivalent rate: " + peak_src + " (max over: " + "; ".join(f"{n} = {v:.0f}" for v, n in cands) + ")"
     # DRAM traffic of the dominant kernel: ncu cannot run inside the bench, so this is the committed
     # `ncu --set full` capture of the same four GEMM shapes at M = 16384 (bytes per launch, averaged
     # over the step's shape mix), labelled as such
@@ -452,6 +455,7 @@ def main():
                 "unit": "TOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "peak_int8_library_burst": int8_burst, "frac_int8_library_burst": (achieved / int8_burst) if int8_burst else None,
+                "peak_int8_library_sustained": int8_sustained, "frac_int8_library_sustained": (achieved / int8_sustained) if int8_sustained else None,
                 "peak_2x_bf16_burst": 2.0 * bf16_burst, "frac_2x_bf16_burst": achieved / (2.0 * bf16_burst),
                 "peak_2x_bf16_sustained": 2.0 * bf16_sus, "frac_2x_bf16_sustained": achieved / (2.0 * bf16_sus),
                 "peak_nominal": 4500.0, "frac_nominal": achieved / 4500.0,

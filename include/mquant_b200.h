@@ -86,6 +86,16 @@ int mq_act_fake_quant_f16(const void* x, int64_t ldx, void* y, int64_t ldy,
 int mq_act_quant_i8_dynamic(const void* x, int64_t ldx, int8_t* q, float* srow_out, int64_t M,
                             int n_in, int n_out, float clip_ratio, void* stream);
 
+/* RMS normalisation fused with the static quantiser (RMSN.forward,
+ * fake_quant/module_util.py:42-61, followed by the ActQuantizer of the Linears that read it):
+ *   r_m = 1 / sqrt( sum_c float(x[m,c])^2 / mean_dim + eps )      (fp32)
+ *   y[m,c] = fp16( float(x[m,c]) * r_m )                          (nullable: plain RMSN when q is NULL)
+ *   q[m,c] = clamp(rne(y[m,c] / s_m), -128, 127), zero for C <= c < n_out; s_m by modality as
+ *   in mq_act_quant_i8 (srow_out nullable).  ldy = C. */
+int mq_rmsn_quant_i8(const void* x, int64_t ldx, int8_t* q, void* y_f16, float* srow_out,
+                     const uint8_t* modality, const float* scales, int64_t M, int C, int n_out,
+                     float mean_dim, float eps, void* stream);
+
 /* ---- (a) online Hadamard, fused with the quantiser ------------------------------------- */
 
 /* y = x . (hadK (x) H_{n/had_k})^T / sqrt(n)  (matmul_hadU_cuda, hadamard_utils.py:115-128),

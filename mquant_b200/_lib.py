@@ -29,6 +29,7 @@ SIGNATURES = {
     "mq_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "mq_act_quant_i8": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i, _i, _u, _p]),
     "mq_act_fake_quant_f16": (_i, [_p, _i64, _p, _i64, _p, _p, _i, _i, _i64, _i, _p]),
+    "mq_rmsn_quant_i8": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i, _i, C.c_float, C.c_float, _p]),
     "mq_act_quant_i8_dynamic": (_i, [_p, _i64, _p, _p, _i64, _i, _i, C.c_float, _p]),
     "mq_hadamard_quant_i8": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _u, _p]),
     "mq_hadamard_transform_f16": (_i, [_p, _i64, _p, _i64, _i64, _i, C.c_float, _p]),

@@ -96,6 +96,24 @@ def act_quant_i8(x, scales, modality=None, n_out=None, split=False, want_row_sca
 
 
 @_on_device
+def rmsn_quant_i8(x, mean_dim, eps, scales=None, modality=None, n_out=None, want_codes=True, want_f16=False,
+                  want_row_scales=True):
+    """mq_rmsn_quant_i8: RMSN (fake_quant/module_util.py:42-61) fused with the static INT8 quantiser.
+    x: [..., C] fp16.  Returns dict(y=fp16 [M, C] | None, q=int8 [M, n_out] | None, s_row)."""
+    _need_cuda(x, scales, modality)
+    assert x.dtype == torch.float16, "activations must be fp16"
+    x2 = _as_rows(x)
+    M, C = x2.shape
+    n_out = C if n_out is None else n_out
+    y = torch.empty((M, C), dtype=torch.float16, device=x.device) if want_f16 else None
+    q = torch.empty((M, n_out), dtype=torch.int8, device=x.device) if want_codes else None
+    srow = torch.empty((M,), dtype=torch.float32, device=x.device) if (want_codes and want_row_scales) else None
+    check(lib().mq_rmsn_quant_i8(_ptr(x2), _ld(x2), _ptr(q), _ptr(y), _ptr(srow), _ptr(modality), _ptr(scales), M, C,
+                                 n_out, float(mean_dim), float(eps), _stream()), "mq_rmsn_quant_i8")
+    return {"y": y, "q": q, "s_row": srow}
+
+
+@_on_device
 def act_fake_quant(x, scales, modality=None, bits=8, per_channel=False, out=None):
     """mq_act_fake_quant_f16: quant->dequant, same shape/dtype as x."""
     _need_cuda(x, scales, modality)

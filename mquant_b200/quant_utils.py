@@ -266,6 +266,15 @@ class ActQuantizer(torch.nn.Module):
 
 # ---- the wrapper ------------------------------------------------------------------------------
 
+def _prequant_of(x, scales, n_out, modality):
+    """INT8 codes an RMSNQuant attached to its output (module_util.py), if they are exactly what
+    this consumer would compute: same scale buffer, same padded width, same modality mask."""
+    pre = getattr(x, "_mq_prequant", None)
+    if pre is not None and pre.matches(scales, n_out, modality):
+        return pre.q, pre.s_row
+    return None
+
+
 def _round_up(a, b):
     return (a + b - 1) // b * b
 
@@ -406,8 +415,12 @@ class ActQuantWrapper(torch.nn.Module):
             if q.shape[1] != pk["Kp"]:
                 q = torch.nn.functional.pad(q, (0, pk["Kp"] - q.shape[1]))
         else:
-            q, srow, x0 = ops.act_quant_i8(x2, scales, modality, n_out=pk["Kp"], split=self.split,
-                                           want_row_scales=modality is not None)
+            pre = None if self.split else _prequant_of(x, scales, pk["Kp"], modality)
+            if pre is not None:  # codes emitted by the RMSNQuant in front (module_util.py)
+                q, srow, x0 = pre[0], pre[1], None
+            else:
+                q, srow, x0 = ops.act_quant_i8(x2, scales, modality, n_out=pk["Kp"], split=self.split,
+                                               want_row_scales=modality is not None)
         s_a = srow if modality is not None else scales[0:1]
         out = ops.w4a8_gemm(q, pk["w4"], s_a, pk["s_w"], pk["N"], bias=pk["bias"], x0=x0, w0=pk["w0"])
         return out.reshape(*x.shape[:-1], pk["N"])
@@ -786,8 +799,12 @@ class _SiblingGroup:
                 x2 = x2.clamp(-65504.0, 65504.0).to(torch.float16)
             scales = qz.device_scales(x.device)
             modality = w.quantizer._modality(x) if qz.scale_visual is not None else None
-            q, srow, _ = ops.act_quant_i8(x2, scales, modality, n_out=self.Kp, split=False,
-                                          want_row_scales=modality is not None)
+            pre = _prequant_of(x, scales, self.Kp, modality)
+            if pre is not None:
+                q, srow = pre
+            else:
+                q, srow, _ = ops.act_quant_i8(x2, scales, modality, n_out=self.Kp, split=False,
+                                              want_row_scales=modality is not None)
             s_a = srow if modality is not None else scales[0:1]
             self._out = ops.w4a8_gemm(q, self.w4, s_a, self.s_w, self.N, bias=self.bias)
             self._x, self._ver, self._served = x, ver, set()
@@ -807,8 +824,12 @@ def _forward_single(self, member, x):
         x2 = x2.clamp(-65504.0, 65504.0).to(torch.float16)
     scales = qz.device_scales(x.device)
     modality = member.quantizer._modality(x) if qz.scale_visual is not None else None
-    q, srow, _ = ops.act_quant_i8(x2, scales, modality, n_out=pk["Kp"], split=False,
-                                  want_row_scales=modality is not None)
+    pre = _prequant_of(x, scales, pk["Kp"], modality)
+    if pre is not None:
+        q, srow = pre
+    else:
+        q, srow, _ = ops.act_quant_i8(x2, scales, modality, n_out=pk["Kp"], split=False,
+                                      want_row_scales=modality is not None)
     s_a = srow if modality is not None else scales[0:1]
     out = ops.w4a8_gemm(q, pk["w4"], s_a, pk["s_w"], pk["N"], bias=pk["bias"])
     return out.reshape(*x.shape[:-1], pk["N"])

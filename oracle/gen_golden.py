@@ -333,5 +333,47 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def gen_rmsn():
+    """RMSN.forward (fake_quant/module_util.py:42-61) followed by a static ActQuantizer
+    (quant_utils.py:97-179), as in front of q/k/v and w1/w2 once the LayerNorm weights are fused
+    into the Linears (rotation_utils.py fuse_layer_norms).  Separate entry point so that the
+    other fixtures need not be regenerated: ``python oracle/gen_golden.py rmsn``."""
+    from oracle._ref_import import import_reference
+
+    qu, hu = import_reference()
+    import torch
+    from fake_quant.module_util import RMSN
+
+    torch.manual_seed(4242)
+    torch.set_num_threads(1)
+    case = {}
+    for tag, M, C in (("h4096", 20, 4096), ("h3584", 9, 3584), ("h1000", 7, 1000)):
+        x = (torch.randn(M, C) * 2.5)
+        x[:, 5] *= 30
+        x[M // 2] *= 0.01  # one quiet token: eps matters
+        x = x.to(torch.float16)
+        ln = RMSN(C, eps=1e-6 if C == 3584 else 1e-5)
+        y = ln(x)
+        q = qu.ActQuantizer()
+        q.configure(bits=8, sym=True, static=True, observer_type="minmax", calibration_mode="layer_wise")
+        q.calibrate, q.quant = True, False
+        q(y[: M // 2])
+        q.last_calibrate = True
+        q(y[M // 2:])
+        q.calibrate, q.quant, q.last_calibrate = False, True, False
+        fq = q(y)
+        scale = q.quantizer.scale.float()
+        case[f"{tag}_x"] = x.numpy()
+        case[f"{tag}_eps"] = np.float32(ln.eps)
+        case[f"{tag}_y"] = y.numpy()
+        case[f"{tag}_scale"] = scale.numpy()
+        case[f"{tag}_codes"] = torch.round(fq.float() / scale).to(torch.int8).numpy()  # exact: fq = code * scale in fp16
+    np.savez_compressed(os.path.join(OUT, "rmsn.npz"), **case)
+    print("rmsn.npz", os.path.getsize(os.path.join(OUT, "rmsn.npz")))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "rmsn":
+        gen_rmsn()
+    else:
+        main()

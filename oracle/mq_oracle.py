@@ -515,6 +515,16 @@ def qlinear_int(codes_a, s_a, codes_w, s_w, bias=None, x0=None, w0=None):
 # ----------------------------------------------------------------------------------
 
 
+def rmsn(x, mean_dim, eps=1e-5):
+    """RMSN.forward (fake_quant/module_util.py:55-61) for fp16 input: fp32 arithmetic, fp16 result.
+    (np.sum's pairwise fp32 summation is ONE valid order of torch's reduction; tests compare within
+    the stated ulp budget.)"""
+    xf = np.asarray(x, F16).astype(F32)
+    variance = (xf * xf).sum(-1, keepdims=True, dtype=F32) / F32(mean_dim)
+    r = F32(1.0) / np.sqrt(variance + F32(eps), dtype=F32)
+    return (xf * r).astype(F16)
+
+
 def dynamic_per_token_scales(x, bits=8, clip_ratio=1.0):
     """find_params, per-token symmetric (:236-250): min/max with 0 in fp32 (``tmp`` fp32),
     times clip_ratio, scale = xmax / maxq, rows that are all zero get scale 1."""

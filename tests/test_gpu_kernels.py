@@ -224,6 +224,61 @@ def test_percentile_observer(ops, golden):
     assert got[0] == O.torch_quantile_f32(flat, 1.0 - 0.99999)
 
 
+# ------------------------------------------------------------------------------- rmsn -> quant
+@pytest.mark.parametrize("tag", ["h4096", "h3584", "h1000"])
+def test_rmsn_quant_golden(ops, golden, tag):
+    """mq_rmsn_quant_i8 vs the reference's RMSN + ActQuantizer (tests/golden/rmsn.npz).  The fp32 sum
+    of squares runs in another order than torch's: the fp16 result may move by one ulp on < 1e-3 of
+    the elements; the quantiser is bit-exact on OUR normalised values, and the end-to-end codes are
+    the reference's up to +-1 on < 2e-3 of the elements."""
+    g = golden("rmsn")
+    x, yref, scale, eps = g[tag + "_x"], g[tag + "_y"], g[tag + "_scale"], float(g[tag + "_eps"])
+    M, C = x.shape
+    n_out = (C + 127) // 128 * 128
+    scales = ops.make_scales(float(scale), None, "cuda")
+    r = ops.rmsn_quant_i8(dev(x), C, eps, scales=scales, n_out=n_out, want_codes=True, want_f16=True)
+    y, q = host(r["y"]), host(r["q"])
+    d = np.abs(bits16(y).astype(np.int32) - bits16(yref).astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())
+    assert np.array_equal(q[:, :C], O.act_quant_codes(y, scale).astype(np.int8))
+    assert not q[:, C:].any()
+    dc = np.abs(q[:, :C].astype(np.int32) - g[tag + "_codes"].astype(np.int32))
+    assert dc.max() <= 1 and (dc > 0).mean() < 2e-3
+    assert np.array_equal(host(r["s_row"]), np.full(M, scale, np.float32))
+    # plain RMSN (no codes) gives the same fp16 tensor
+    y2 = host(ops.rmsn_quant_i8(dev(x), C, eps, want_codes=False, want_f16=True)["y"])
+    assert np.array_equal(bits16(y2), bits16(y))
+
+
+@pytest.mark.parametrize("C", [4096, 5120, 8192, 2560])
+def test_rmsn_quant_fused_equals_unfused(ops, C):
+    """At the benchmark's row count: the fused kernel against RMSN followed by mq_act_quant_i8 (codes,
+    per-token MSQ scales: bit-identical) and against the oracle on sampled rows."""
+    M = 16384
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = torch.randn(M, C, device="cuda", generator=g) * 3
+    x[:, 11] *= 50
+    x = x.half()
+    mod = (torch.rand(M, device="cuda", generator=g) < 0.4).to(torch.uint8)
+    s, sv = float(torch.tensor(0.0213, dtype=torch.float16)), float(torch.tensor(0.0571, dtype=torch.float16))
+    scales = ops.make_scales(s, sv, "cuda")
+    fused = ops.rmsn_quant_i8(x, C, 1e-6, scales=scales, modality=mod, want_codes=True, want_f16=True)
+    y = ops.rmsn_quant_i8(x, C, 1e-6, want_codes=False, want_f16=True)["y"]
+    q, srow, _ = ops.act_quant_i8(y, scales, mod)
+    assert torch.equal(fused["y"].view(torch.int16), y.view(torch.int16))
+    assert torch.equal(fused["q"], q) and torch.equal(fused["s_row"], srow)
+    rows = np.random.default_rng(C).integers(0, M, 48)
+    ridx = torch.from_numpy(rows).cuda()
+    yo = O.rmsn(host(x[ridx]), C, 1e-6)
+    d = np.abs(bits16(host(y[ridx])).astype(np.int32) - bits16(yo).astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+    # a non-fp16-valued scale takes the quantiser with the division fallback: still bit-exact
+    scales2 = ops.make_scales(0.0213, 0.0571, "cuda")
+    f2 = ops.rmsn_quant_i8(x[:512], C, 1e-6, scales=scales2, modality=mod[:512], want_codes=True, want_f16=False)
+    q2, _, _ = ops.act_quant_i8(y[:512], scales2, mod[:512])
+    assert torch.equal(f2["q"], q2)
+
+
 # ------------------------------------------------------------------------------- hadamard
 def had_check(ops, x, n, had_k, s_act, fp32_had=False, split=False, modality=None, s_vis=None):
     from mquant_b200 import hadamard_utils as hu

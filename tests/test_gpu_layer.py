@@ -366,6 +366,47 @@ def test_sibling_fusion_is_bit_identical(qu):
 
 
 @torch.no_grad()
+def test_rmsn_quant_feeds_sibling_groups(qu):
+    """SURVEY.md 8(f-3): an RMSNQuant in front of q/k/v (w1/w2) emits the codes the fused GEMM reads;
+    outputs are bit-identical to RMSN -> wrapper, with and without the fp16 store, and a consumer
+    with other scales (or a tensor that did not come from the norm) quantises by itself."""
+    from mquant_b200 import module_util as mu, msq
+    from mquant_b200.prefill import QuantLinearStack
+
+    stack = QuantLinearStack("qwenvl-9.6b", n_layers=1, device="cuda", calib_tokens=256, fuse_siblings=True)
+    blk = stack.layers[0]
+    inputs = stack.make_inputs(300, "cuda", seed=5, seq_len=100, visual_span=40)
+    h = inputs["h"] * 7  # an un-normalised hidden state
+    norm = mu.RMSN(4096, eps=1e-6).cuda()
+    with msq.modality_context(inputs["mask"]):
+        y = norm(h)
+        ref = {k: blk[k](y).clone() for k in ("attn_q_proj", "attn_k_proj", "attn_v_proj")}
+        ref_mlp = {k: blk[k](y).clone() for k in ("mlp_w1", "mlp_w2")}
+        for emit_y in (True, False):
+            nq = mu.RMSNQuant(4096, eps=1e-6, consumer=blk["attn_k_proj"], emit_y=emit_y).cuda()
+            yq = nq(h)
+            assert hasattr(yq, "_mq_prequant")
+            if emit_y:
+                assert torch.equal(yq.view(torch.int16), y.view(torch.int16))
+            for k, v in ref.items():
+                assert torch.equal(blk[k](yq).contiguous().view(torch.int16), v.view(torch.int16)), (k, emit_y)
+        # the MLP pair has its own scales: codes made for q/k/v must not be used
+        nq = mu.RMSNQuant(4096, eps=1e-6, consumer=blk["attn_q_proj"]).cuda()
+        yq = nq(h)
+        same_scales = torch.equal(blk["mlp_w1"].quantizer.quantizer.scale.float().cpu(),
+                                  blk["attn_q_proj"].quantizer.quantizer.scale.float().cpu())
+        assert not same_scales
+        for k, v in ref_mlp.items():
+            assert torch.equal(blk[k](yq).contiguous().view(torch.int16), v.view(torch.int16)), k
+    # calibration / fake-quant mode: the norm falls back to the plain kernel
+    blk["attn_q_proj"].real_quant = False
+    try:
+        assert not hasattr(mu.RMSNQuant(4096, eps=1e-6, consumer=blk["attn_q_proj"]).cuda()(h), "_mq_prequant")
+    finally:
+        blk["attn_q_proj"].real_quant = True
+
+
+@torch.no_grad()
 def test_bf16_activations(qu):
     """InternVL2 / Qwen2-VL run in bf16.  The kernels take fp16 (an in-range bf16 value converts
     exactly), statistics and scales stay in bf16 like the reference's, the fake-quant output is

@@ -225,3 +225,16 @@ def test_bf16_activations_match_reference(golden):
     codes, y = O.act_fake_quant_bf16(g["x"], g["scale"].reshape(()))
     assert np.array_equal(codes, g["codes"])
     assert np.array_equal(y, g["y"])
+
+
+@pytest.mark.parametrize("tag", ["h4096", "h3584", "h1000"])
+def test_rmsn_oracle_matches_reference(golden, tag):
+    """oracle.rmsn vs RMSN.forward of the reference (fake_quant/module_util.py:42-61) run on the CPU;
+    np.sum and torch.sum add the 4096 squares in different orders: <= 1 fp16 ulp on < 1e-3 of the
+    elements.  The codes follow from the reference's own fp16 tensor exactly."""
+    g = golden("rmsn")
+    x, y = g[tag + "_x"], g[tag + "_y"]
+    yo = O.rmsn(x, x.shape[1], float(g[tag + "_eps"]))
+    d = np.abs(yo.view(np.uint16).astype(np.int32) - y.view(np.uint16).astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+    assert np.array_equal(O.act_quant_codes(y, g[tag + "_scale"]).astype(np.int8), g[tag + "_codes"])

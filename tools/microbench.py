@@ -107,6 +107,13 @@ def main():
             if want("quant"):
                 sec, best = timeit(lambda: ops.act_quant_i8(x, scales, mod))
                 rec("act_quant_i8_msq", f"{M}x{C}", sec, best, bytes_=3 * M * C + M)
+            if want("rmsn"):
+                sec, best = timeit(lambda: ops.rmsn_quant_i8(x, C, 1e-6, scales=scales, modality=mod, want_codes=True,
+                                                             want_f16=False))
+                rec("rmsn_quant_i8", f"{M}x{C}", sec, best, bytes_=3 * M * C + M)
+                sec, best = timeit(lambda: ops.rmsn_quant_i8(x, C, 1e-6, scales=scales, modality=mod, want_codes=True,
+                                                             want_f16=True))
+                rec("rmsn_quant_i8+y", f"{M}x{C}", sec, best, bytes_=5 * M * C + M)
             if want("fake"):
                 sec, best = timeit(lambda: ops.act_fake_quant(x, scales, mod))
                 rec("act_fake_quant", f"{M}x{C}", sec, best, bytes_=4 * M * C + M)
