@@ -202,6 +202,26 @@ int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4, const floa
                     const void* w0, void* out, int64_t ldo, int64_t M, int64_t N, int64_t K,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- (f-2) GPTQ acceleration --------------------------------------------------------------- */
+
+/* GPTQ.add_batch (fake_quant/gptq/gptq_utils.py:182-195): H = alpha * H + beta * X^T X with
+ * alpha = n / (n + t), beta = 2 / (n + t).  x: [T, C] fp16 (row stride ldx), H: [C, C] fp32,
+ * contiguous.  fp16 x fp16 products are exact in fp32; the sums run on the tensor core in fp32. */
+int mq_gptq_hessian_update(const void* x, int64_t ldx, int64_t T, int C, float* H, float alpha,
+                           float beta, void* stream);
+
+/* Inner loop of GPTQ.fasterquant (gptq_utils.py:254-283) for one block of `count` <= 128 columns,
+ * symmetric per-row scales (WeightQuantizer.quantize -> sym_quant_dequant, quant_utils.py:42-57):
+ *   for i: q = scale * clamp(round(w_i / scale), -(maxq+1), maxq);  Q[:, i] = q
+ *          Losses[:, i] = (w_i - q)^2 / d^2;  err = (w_i - q) / d,  d = Hinv1[i, i];  Err[:, i] = err
+ *          w[i:] -= err * Hinv1[i, i:]
+ * W points at the block's first column (row stride ldw) and is updated in place; Hinv1 at the
+ * block's diagonal element of the upper Cholesky factor (row stride ldh).  Every operation is an
+ * fp32 operation in the reference's order. */
+int mq_gptq_block_f32(float* W, int64_t ldw, const float* Hinv1, int64_t ldh, const float* scale,
+                      float maxq, float* Q, float* Err, float* Losses, int rows, int count,
+                      void* stream);
+
 /* Which kernel mq_w4a8_gemm_ws runs for a shape and workspace size: 1 = weight-streaming dp4a
  * (decode), 2 = split-K tcgen05, 3 = 128 x 256 tcgen05, 4 = 256 x 256 tcgen05; 0 = invalid
  * shape.  Pure function of its arguments and the SM count (diagnostics / tests). */

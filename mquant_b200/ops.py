@@ -96,6 +96,39 @@ def act_quant_i8(x, scales, modality=None, n_out=None, split=False, want_row_sca
 
 
 @_on_device
+def gptq_hessian_update(x, H, nsamples_before, batch):
+    """mq_gptq_hessian_update: GPTQ.add_batch (fake_quant/gptq/gptq_utils.py:182-195) on the rows of
+    x ([T, C] fp16): H <- H * n/(n+t) + 2/(n+t) X^T X with n = nsamples_before, t = batch.  In place."""
+    _need_cuda(x, H)
+    assert x.dtype == torch.float16 and H.dtype == torch.float32 and H.is_contiguous()
+    x2 = _as_rows(x)
+    T, C = x2.shape
+    assert H.shape == (C, C)
+    n1 = nsamples_before + batch
+    check(lib().mq_gptq_hessian_update(_ptr(x2), _ld(x2), T, C, _ptr(H), float(nsamples_before) / n1, 2.0 / n1, _stream()),
+          "mq_gptq_hessian_update")
+    return H
+
+
+@_on_device
+def gptq_block(W, i1, i2, Hinv, scale, maxq):
+    """mq_gptq_block_f32 on the columns i1:i2 of W ([rows, columns] fp32, updated in place) with the
+    upper Cholesky factor Hinv.  Returns (Q1, Err1, Losses1), each [rows, i2 - i1]."""
+    _need_cuda(W, Hinv, scale)
+    assert W.dtype == torch.float32 and Hinv.dtype == torch.float32 and W.stride(1) == 1 and Hinv.stride(1) == 1
+    rows, count = W.shape[0], i2 - i1
+    scale = scale.reshape(-1).to(torch.float32).contiguous()
+    assert scale.numel() == rows
+    Q = torch.empty((rows, count), dtype=torch.float32, device=W.device)
+    Err = torch.empty_like(Q)
+    Losses = torch.empty_like(Q)
+    wv, hv = W[:, i1:i2], Hinv[i1:i2, i1:i2]
+    check(lib().mq_gptq_block_f32(wv.data_ptr(), W.stride(0), hv.data_ptr(), Hinv.stride(0), _ptr(scale), float(maxq),
+                                  _ptr(Q), _ptr(Err), _ptr(Losses), rows, count, _stream()), "mq_gptq_block_f32")
+    return Q, Err, Losses
+
+
+@_on_device
 def rmsn_quant_i8(x, mean_dim, eps, scales=None, modality=None, n_out=None, want_codes=True, want_f16=False,
                   want_row_scales=True):
     """mq_rmsn_quant_i8: RMSN (fake_quant/module_util.py:42-61) fused with the static INT8 quantiser.
@@ -118,6 +151,21 @@ def act_fake_quant(x, scales, modality=None, bits=8, per_channel=False, out=None
     """mq_act_fake_quant_f16: quant->dequant, same shape/dtype as x."""
     _need_cuda(x, scales, modality)
     assert x.dtype == torch.float16
+    if x.shape[-1] % 8 != 0 and not per_channel and modality is None:
+        # one scale for the whole tensor and a last dimension the 128-bit accesses cannot take (the
+        # patch-embedding convolutions see [B, 3, H, W]): element-wise, so any 2-D view will do --
+        # flatten, pad to a multiple of 8 and pick the widest power-of-two row that divides it
+        flat = x.reshape(-1)
+        n = flat.numel()
+        n8 = (n + 7) // 8 * 8
+        if n8 != n:
+            flat = torch.nn.functional.pad(flat, (0, n8 - n))
+        width = min(n8 & -n8, 4096)
+        y = act_fake_quant(flat.reshape(-1, width), scales, None, bits, False).reshape(-1)[:n].reshape(x.shape)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
     x2 = _as_rows(x)
     M, C = x2.shape
     y = torch.empty((M, C), dtype=torch.float16, device=x.device) if out is None else out.reshape(M, C)

@@ -372,8 +372,53 @@ def gen_rmsn():
     print("rmsn.npz", os.path.getsize(os.path.join(OUT, "rmsn.npz")))
 
 
+def gen_gptq():
+    """GPTQ (fake_quant/gptq/gptq_utils.py:171-310) on one small Linear, on the CPU: Hessian after
+    three add_batch calls, WeightQuantizer scales and the final fake-quantised weight.
+    ``python oracle/gen_golden.py gptq`` (unfoldNd, used by GPTQConv only, is absent: stubbed)."""
+    import types
+
+    from oracle._ref_import import import_reference
+
+    qu, hu = import_reference()
+    import torch
+
+    if "unfoldNd" not in sys.modules:
+        m = types.ModuleType("unfoldNd")
+        m.UnfoldNd = object
+        sys.modules["unfoldNd"] = m
+    from fake_quant.gptq.gptq_utils import GPTQ
+
+    torch.manual_seed(7)
+    torch.set_num_threads(1)
+    rows, cols = 96, 256
+    layer = torch.nn.Linear(cols, rows, bias=False)
+    layer.weight.data = (torch.randn(rows, cols) * 0.05).half().float()
+    W0 = layer.weight.data.clone()
+    g = GPTQ(layer)
+    g.quantizer = qu.WeightQuantizer()
+    g.quantizer.configure(4, perchannel=True, sym=True, mse=False)
+    basis = torch.randn(cols, cols) / cols ** 0.5  # correlated inputs: the Hessian is far from diagonal
+    xs = []
+    for b in range(3):
+        x = ((torch.randn(2, 64, cols) @ basis) * (1 + 3 * torch.rand(cols))).half()
+        xs.append(x)
+        g.add_batch(x, None)
+    H = g.H.clone()
+    torch.cuda.synchronize = lambda *a, **k: None  # (fasterquant calls it unconditionally, :285; no device here)
+    g.fasterquant(percdamp=0.01, groupsize=-1)
+    case = {"W0": W0.numpy(), "H": H.numpy(), "nsamples": np.int64(g.nsamples), "scale": g.quantizer.scale.reshape(-1).numpy(),
+            "Wq": layer.weight.data.numpy()}
+    for b, x in enumerate(xs):
+        case[f"x{b}"] = x.numpy()
+    np.savez_compressed(os.path.join(OUT, "gptq.npz"), **case)
+    print("gptq.npz", os.path.getsize(os.path.join(OUT, "gptq.npz")))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "rmsn":
         gen_rmsn()
+    elif len(sys.argv) > 1 and sys.argv[1] == "gptq":
+        gen_gptq()
     else:
         main()

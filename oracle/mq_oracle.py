@@ -515,6 +515,37 @@ def qlinear_int(codes_a, s_a, codes_w, s_w, bias=None, x0=None, w0=None):
 # ----------------------------------------------------------------------------------
 
 
+def gptq_hessian(H, nsamples, x, batch):
+    """GPTQ.add_batch (fake_quant/gptq/gptq_utils.py:182-195) in float64 (the check value for the
+    fp32 tensor-core sum): returns (H', nsamples')."""
+    x = np.asarray(x, F16).astype(np.float64).reshape(-1, x.shape[-1])
+    n1 = nsamples + batch
+    return np.asarray(H, np.float64) * (nsamples / n1) + (2.0 / n1) * (x.T @ x), n1
+
+
+def gptq_block(W1, Hinv1, scale, maxq):
+    """The column loop of GPTQ.fasterquant for one block (gptq_utils.py:254-283), fp32 operation by
+    fp32 operation: q = scale * clamp(round(w / scale), -(maxq+1), maxq) (quant_utils.py:42-57),
+    Losses = (w - q)^2 / d^2, err = (w - q) / d, W1[:, i:] -= err (x) Hinv1[i, i:] (rounded product,
+    rounded difference).  Returns (W1', Q1, Err1, Losses1)."""
+    W1 = np.array(W1, F32)
+    Hinv1 = np.asarray(Hinv1, F32)
+    s = np.asarray(scale, F32).reshape(-1)
+    count = W1.shape[1]
+    Q1, Err1, L1 = np.zeros_like(W1), np.zeros_like(W1), np.zeros_like(W1)
+    for i in range(count):
+        w = W1[:, i].copy()
+        d = Hinv1[i, i]
+        q = (s * np.clip(np.rint((w / s).astype(F32)), -(maxq + 1), maxq).astype(F32)).astype(F32)
+        diff = (w - q).astype(F32)
+        Q1[:, i] = q
+        L1[:, i] = ((diff * diff).astype(F32) / (d * d).astype(F32)).astype(F32)
+        err = (diff / d).astype(F32)
+        Err1[:, i] = err
+        W1[:, i:] = (W1[:, i:] - (err[:, None] * Hinv1[i, i:][None, :]).astype(F32)).astype(F32)
+    return W1, Q1, Err1, L1
+
+
 def rmsn(x, mean_dim, eps=1e-5):
     """RMSN.forward (fake_quant/module_util.py:55-61) for fp16 input: fp32 arithmetic, fp16 result.
     (np.sum's pairwise fp32 summation is ONE valid order of torch's reduction; tests compare within

@@ -725,3 +725,115 @@ def test_gemm_extreme_codes(ops):
     cw = np.where(np.arange(N)[:, None] % 2 == 0, -8, 7).astype(np.int8) * np.ones((1, K), np.int8)
     case = (qa, cw, np.array([0.01], np.float32), np.full(N, 1e-3, np.float32), None, None, None)
     assert np.array_equal(bits16(run_gemm(ops, case, simt=False)), bits16(oracle_gemm(case)))
+
+
+# ------------------------------------------------------------------------------- GPTQ (f-2)
+def test_gptq_hessian_golden(ops, golden):
+    """mq_gptq_hessian_update vs GPTQ.add_batch of the reference (tests/golden/gptq.npz): three
+    batches accumulated in place.  fp16 x fp16 products are exact in fp32; only the order of the
+    fp32 additions differs from the reference's matmul."""
+    g = golden("gptq")
+    C = g["H"].shape[0]
+    H = torch.zeros((C, C), dtype=torch.float32, device="cuda")
+    H64, n = np.zeros((C, C)), 0
+    for b in range(3):
+        x = g[f"x{b}"]
+        ops.gptq_hessian_update(dev(x), H, n, x.shape[0])
+        H64, n = O.gptq_hessian(H64, n, x, x.shape[0])
+    assert n == int(g["nsamples"])
+    top = np.abs(g["H"]).max()
+    assert np.abs(host(H) - g["H"]).max() <= 2e-6 * top
+    assert np.abs(host(H) - H64).max() <= 2e-6 * top
+    assert np.array_equal(host(H), host(H).T)  # tile (i, j) and tile (j, i) add in the same order
+
+
+@pytest.mark.parametrize("T,C,ld", [(1, 8, 8), (63, 136, 136), (1000, 4096, 4096), (4100, 1032, 1040), (2048, 11008, 11008)])
+def test_gptq_hessian_shapes(ops, T, C, ld):
+    """Ragged token counts, C not a multiple of the 128 x 256 tile, strided rows, the benchmark's
+    widths; against a float64 X^T X on sampled rows of H."""
+    rng = np.random.default_rng(T + C)
+    xs = torch.zeros((T, ld), dtype=torch.float16, device="cuda")
+    xs[:, :C] = dev((rng.standard_normal((T, C)) * (1 + 4 * rng.random(C))).astype(np.float16))
+    x = xs[:, :C]
+    H0 = dev(rng.standard_normal((C, C)).astype(np.float32))
+    H = H0.clone()
+    n0, t = 5, 3
+    ops.gptq_hessian_update(x, H, n0, t)
+    rows = torch.from_numpy(rng.choice(C, size=min(C, 64), replace=False)).cuda()
+    x64 = x.double()
+    want = H0[rows].double() * (n0 / (n0 + t)) + (2.0 / (n0 + t)) * (x64[:, rows].t() @ x64)
+    err = (H[rows].double() - want).abs().max().item()
+    # fp32-grade: within a small multiple of the error of the reference's own fp32 matmul
+    assert err <= 4e-6 * want.abs().max().item(), err
+    ops.gptq_hessian_update(x[:0], H, n0, t)  # no tokens: H untouched (the reference would only rescale by n/(n+0))
+
+
+@pytest.mark.parametrize("rows,count", [(1, 1), (96, 128), (300, 128), (4096, 128), (257, 40)])
+def test_gptq_block_bit_exact(ops, rows, count):
+    """mq_gptq_block_f32 vs oracle.gptq_block (the reference's column loop, fp32 operation by fp32
+    operation): W1, Q1, Err1, Losses1 bit-identical.  W and Hinv are views into wider matrices."""
+    rng = np.random.default_rng(rows * 131 + count)
+    cols = count + 72
+    W = (rng.standard_normal((rows, cols)) * 0.05).astype(np.float32)
+    A = rng.standard_normal((cols, 2 * cols)).astype(np.float32)
+    Hinv = np.linalg.cholesky((A @ A.T / (2 * cols) + 0.05 * np.eye(cols)).astype(np.float32)).T.astype(np.float32)
+    scale = (np.abs(W).max(axis=1) / 7).astype(np.float32)
+    i1, i2 = 8, 8 + count
+    Wd = dev(W)
+    Q, Err, Losses = ops.gptq_block(Wd, i1, i2, dev(Hinv), dev(scale), 7)
+    W1, Q1, Err1, L1 = O.gptq_block(W[:, i1:i2], Hinv[i1:i2, i1:i2], scale, 7)
+    for name, got, want in (("Q", Q, Q1), ("Err", Err, Err1), ("Losses", Losses, L1), ("W", Wd[:, i1:i2], W1)):
+        assert np.array_equal(host(got).view(np.uint32), want.view(np.uint32)), name
+    untouched = np.ones(cols, bool)
+    untouched[i1:i2] = False
+    assert np.array_equal(host(Wd)[:, untouched], W[:, untouched])
+
+
+def test_gptq_fasterquant_matches_reference_golden(ops, golden):
+    """mquant_b200.gptq.GPTQ (add_batch + fasterquant on the kernels) on the reference's golden case:
+    the quantised weight is the reference's up to the entries a differently rounded Cholesky factor
+    flips, the GPTQ objective tr(D H D^T) agrees, and with the SAME factor the kernel loop is
+    bit-identical to the reference's eager loop."""
+    from mquant_b200 import gptq as G, quant_utils as qu
+
+    g = golden("gptq")
+    rows, cols = g["W0"].shape
+    layer = torch.nn.Linear(cols, rows, bias=False).cuda()
+    layer.weight.data = dev(g["W0"])
+    gp = G.GPTQ(layer)
+    gp.quantizer = qu.WeightQuantizer()
+    gp.quantizer.configure(4, perchannel=True, sym=True, mse=False)
+    for b in range(3):
+        gp.add_batch(dev(g[f"x{b}"]), None)
+    assert gp.nsamples == int(g["nsamples"])
+    Hd = gp.H.clone()
+    gp.fasterquant(percdamp=0.01, groupsize=-1)
+    assert np.array_equal(host(gp.quantizer.scale).reshape(-1).view(np.uint32), g["scale"].view(np.uint32))
+    Wq = host(layer.weight.data)
+    assert (Wq != g["Wq"]).mean() < 0.02
+
+    def loss(Wx):
+        D = (g["W0"] - Wx).astype(np.float64)
+        return float(np.einsum("ij,jk,ik->", D, g["H"].astype(np.float64), D))
+
+    assert abs(loss(Wq) / loss(g["Wq"]) - 1) < 0.02
+    # the reference's loop (gptq_utils.py:230-290) in eager torch on the same device and factor
+    W = dev(g["W0"]).clone()
+    H = Hd.clone()
+    H.diagonal().add_(0.01 * torch.mean(torch.diag(H)))
+    Hinv = torch.linalg.cholesky(torch.cholesky_inverse(torch.linalg.cholesky(H)), upper=True)
+    s = gp.quantizer.scale.reshape(-1, 1)
+    Qe = torch.zeros_like(W)
+    for i1 in range(0, cols, 128):
+        i2 = min(i1 + 128, cols)
+        W1, Hinv1 = W[:, i1:i2].clone(), Hinv[i1:i2, i1:i2]
+        Err1 = torch.zeros_like(W1)
+        for i in range(i2 - i1):
+            w, d = W1[:, i], Hinv1[i, i]
+            q = (s * torch.clamp(torch.round(w.unsqueeze(1) / s), -8, 7)).flatten()
+            Qe[:, i1 + i] = q
+            err1 = (w - q) / d
+            W1[:, i:] -= err1.unsqueeze(1).matmul(Hinv1[i, i:].unsqueeze(0))
+            Err1[:, i] = err1
+        W[:, i2:] -= Err1.matmul(Hinv[i1:i2, i2:])
+    assert torch.equal(Qe, layer.weight.data)

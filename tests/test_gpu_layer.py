@@ -366,6 +366,64 @@ def test_sibling_fusion_is_bit_identical(qu):
 
 
 @torch.no_grad()
+def test_aifs_reordered_tokens_through_quantlinear(qu):
+    """the quantized Linears are position-wise, so visual-tokens-first reordering
+    (mquant_b200/aifs.py) with the two-segment modality mask gives bit-identically the reordered
+    outputs, for the plain path and for the fused Hadamard path (down projection)."""
+    from mquant_b200 import aifs, msq
+    from mquant_b200.prefill import QuantLinearStack
+
+    stack = QuantLinearStack("qwenvl-9.6b", n_layers=1, device="cuda", calib_tokens=256)
+    blk = stack.layers[0]
+    B, S = 3, 100
+    inputs = stack.make_inputs(B * S, "cuda", seed=9, seq_len=S, visual_span=30)
+    mask = inputs["mask"].reshape(B, S).bool().cpu()
+    img_pos = []
+    for b in range(B):  # the span of visual tokens of each sequence as (sequence, start marker, end marker)
+        idx = mask[b].nonzero().reshape(-1)
+        img_pos.append((b, int(idx[0]) - 1, int(idx[-1]) + 1))
+    p = aifs.plan(img_pos, S, B, device="cuda")
+    assert torch.equal(aifs.reorder(inputs["mask"].reshape(B, S, 1), p).reshape(-1), aifs.modality_mask(p, S))
+    for key, kind in (("attn_q_proj", "h"), ("mlp_c_proj", "f")):
+        x = inputs[kind].reshape(B, S, -1)
+        with msq.modality_context(inputs["mask"]):
+            ref = blk[key](x.reshape(B * S, -1)).reshape(B, S, -1)
+        with msq.modality_context(aifs.modality_mask(p, S)):
+            out = blk[key](aifs.reorder(x, p).reshape(B * S, -1)).reshape(B, S, -1)
+        assert torch.equal(aifs.restore(out, p).view(torch.int16), ref.view(torch.int16)), key
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("observer", ["minmax", "percentile"])
+def test_conv_wrapper_static_calibration(qu, observer):
+    """The drivers wrap the patch-embedding convolutions and calibrate them layer-wise under
+    --visual_static (quant_utils.py:642-690): a 4-D input with 3 channels must calibrate
+    and give the scale the reference's observer derives from the same tensor."""
+    conv = torch.nn.Conv2d(3, 16, kernel_size=14, stride=14).half().cuda()
+    w = qu.ActQuantWrapper(conv)
+    w.quantizer.configure(bits=8, sym=True, static=True, observer_type=observer, calibration_mode="layer_wise")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    xs = [(torch.randn(2, 3, 28, 28, device="cuda", generator=g) * 2).half() for _ in range(2)]
+    w.quantizer.calibrate, w.quantizer.quant = True, False
+    w(xs[0])
+    w.quantizer.last_calibrate = True
+    y_cal = w(xs[1])
+    w.quantizer.calibrate, w.quantizer.last_calibrate, w.quantizer.quant = False, False, True
+    assert y_cal.shape == (2, 16, 2, 2)
+    scale = float(w.quantizer.quantizer.scale)
+    allx = np.concatenate([x.cpu().numpy().reshape(-1) for x in xs])
+    if observer == "minmax":
+        ref, _ = O.minmax_params(np.float16(allx.min()), np.float16(allx.max()))
+        assert np.float32(scale) == np.float32(ref)
+    else:
+        assert 0 < scale <= float(np.abs(allx).max()) / 127 * 1.01
+    y = w(xs[0])  # quantised forward through the convolution
+    fq = O.act_fake_quant(xs[0].cpu().numpy(), np.float32(scale))
+    yr = torch.nn.functional.conv2d(torch.from_numpy(fq).cuda(), conv.weight, conv.bias, stride=14)
+    assert torch.allclose(y.float(), yr.float(), rtol=2e-3, atol=2e-3)
+
+
+@torch.no_grad()
 def test_rmsn_quant_feeds_sibling_groups(qu):
     """SURVEY.md 8(f-3): an RMSNQuant in front of q/k/v (w1/w2) emits the codes the fused GEMM reads;
     outputs are bit-identical to RMSN -> wrapper, with and without the fp16 store, and a consumer

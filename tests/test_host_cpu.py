@@ -255,3 +255,51 @@ def test_update_all_quantization_params_equals_per_wrapper_update():
                 assert x.dtype == y.dtype and torch.equal(x.reshape(()), y.reshape(())), (name, attr, x, y)
         if a.scale is not None:
             assert torch.equal(a.device_scales(torch.device("cpu")), b.device_scales(torch.device("cpu"))), name
+
+
+def test_aifs_reorder_keeps_causal_attention_invariant():
+    """visual tokens first (model/modeling_qwen_opt.py:717-727, commented sketch).
+    A toy decoder layer (rotary attention + position-wise MLP) on reordered tokens with
+    aifs.causal_mask and permuted rotary phases gives the reordered output of the original layer;
+    the plain lower-triangular mask does not.  After the reorder the MSQ mask is two segments."""
+    import torch
+    from mquant_b200 import aifs
+
+    torch.manual_seed(0)
+    B, S, D, H = 2, 24, 32, 4
+    x = torch.randn(B, S, D, dtype=torch.float64)
+    wq, wk, wv, wo, w1 = (torch.randn(D, D, dtype=torch.float64) / D ** 0.5 for _ in range(5))
+    ang = torch.arange(S, dtype=torch.float64)[:, None] * (1.0 / 10.0 ** (torch.arange(D // H // 2, dtype=torch.float64) / 4))
+    cos, sin = ang.cos().repeat(1, 2), ang.sin().repeat(1, 2)  # [S, D/H]
+
+    def rot(t, c, s):  # t [B,H,S,d]; c, s [B,S,d]
+        t1, t2 = t[..., : t.shape[-1] // 2], t[..., t.shape[-1] // 2:]
+        return t * c[:, None] + torch.cat((-t2, t1), -1) * s[:, None]
+
+    def layer(h, c, s, mask):  # mask [B,S,S] bool
+        def heads(t):
+            return t.reshape(B, S, H, D // H).transpose(1, 2)
+        q, k, v = rot(heads(h @ wq), c, s), rot(heads(h @ wk), c, s), heads(h @ wv)
+        att = (q @ k.transpose(-1, -2)) / (D // H) ** 0.5
+        att = att.masked_fill(~mask[:, None], float("-inf")).softmax(-1)
+        o = (att @ v).transpose(1, 2).reshape(B, S, D) @ wo
+        return h + o + torch.nn.functional.silu((h + o) @ w1)
+
+    cb, sb = cos.expand(B, S, -1), sin.expand(B, S, -1)
+    tril = torch.ones(S, S, dtype=torch.bool).tril().expand(B, S, S)
+    ref = layer(x, cb, sb, tril)
+
+    img_pos = [(0, 3, 12), (1, 0, 7), (1, 15, 20)]  # (sequence, image-start marker, image-end marker)
+    p = aifs.plan(img_pos, S, B)
+    assert p["n_visual"].tolist() == [8, 10]
+    assert p["perm"][0, :8].tolist() == list(range(4, 12)) and p["perm"][0, 8:12].tolist() == [0, 1, 2, 3]
+    xr = aifs.reorder(x, p)
+    assert torch.equal(aifs.restore(xr, p), x)
+    out = layer(xr, aifs.reorder(cb, p), aifs.reorder(sb, p), aifs.causal_mask(p))
+    assert torch.allclose(aifs.restore(out, p), ref, rtol=1e-12, atol=1e-12)
+    wrong = layer(xr, aifs.reorder(cb, p), aifs.reorder(sb, p), tril)
+    assert not torch.allclose(aifs.restore(wrong, p), ref, rtol=1e-6, atol=1e-6)
+    m = aifs.modality_mask(p, S).reshape(B, S)
+    assert m[0].tolist() == [1] * 8 + [0] * 16 and m[1].tolist() == [1] * 10 + [0] * 14
+    with pytest.raises(ValueError):
+        aifs.plan([(0, 5, 40)], S, B)

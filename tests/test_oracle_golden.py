@@ -238,3 +238,47 @@ def test_rmsn_oracle_matches_reference(golden, tag):
     d = np.abs(yo.view(np.uint16).astype(np.int32) - y.view(np.uint16).astype(np.int32))
     assert d.max() <= 1 and (d > 0).mean() < 1e-3
     assert np.array_equal(O.act_quant_codes(y, g[tag + "_scale"]).astype(np.int8), g[tag + "_codes"])
+
+
+def _np_fasterquant(W0, H, scale, maxq=7, blocksize=128, percdamp=0.01):
+    """GPTQ.fasterquant (gptq_utils.py:197-303) with numpy's fp32 LAPACK and oracle.gptq_block."""
+    W = np.array(W0, np.float32)
+    H = np.array(H, np.float32)
+    dead = np.diag(H) == 0
+    H[dead, dead] = 1
+    W[:, dead] = 0
+    H[np.diag_indices_from(H)] += np.float32(percdamp) * np.mean(np.diag(H), dtype=np.float32)
+    L = np.linalg.cholesky(H)
+    Hi = np.linalg.inv(L).T @ np.linalg.inv(L)  # cholesky_inverse
+    Hinv = np.linalg.cholesky(Hi.astype(np.float32)).T.astype(np.float32)  # upper factor
+    Q = np.zeros_like(W)
+    for i1 in range(0, W.shape[1], blocksize):
+        i2 = min(i1 + blocksize, W.shape[1])
+        W1, Q1, Err1, _ = O.gptq_block(W[:, i1:i2], Hinv[i1:i2, i1:i2], scale, maxq)
+        Q[:, i1:i2] = Q1
+        W[:, i2:] -= Err1 @ Hinv[i1:i2, i2:]
+    return Q
+
+
+def test_gptq_oracle_matches_reference(golden):
+    """oracle.gptq_hessian / gptq_block vs GPTQ.add_batch / fasterquant of the reference run on the CPU
+    (tests/golden/gptq.npz).  The Hessian agrees to fp32 summation noise; the quantised weight is the
+    reference's up to the entries a different Cholesky rounding can flip (different LAPACK calls)."""
+    g = golden("gptq")
+    H, n = np.zeros_like(g["H"], dtype=np.float64), 0
+    for b in range(3):
+        x = g[f"x{b}"]
+        H, n = O.gptq_hessian(H, n, x, x.shape[0])
+    assert n == int(g["nsamples"])
+    assert np.abs(H - g["H"]).max() <= 2e-6 * np.abs(g["H"]).max()
+    Q = _np_fasterquant(g["W0"], g["H"], g["scale"])
+    codes = np.rint(Q / g["scale"][:, None])
+    assert np.abs(codes * g["scale"][:, None] - Q).max() == 0 and codes.min() >= -8 and codes.max() <= 7
+    mism = (Q != g["Wq"]).mean()
+    assert mism < 0.02, mism
+
+    def loss(Wq):
+        D = (g["W0"] - Wq).astype(np.float64)
+        return float(np.einsum("ij,jk,ik->", D, g["H"].astype(np.float64), D))
+
+    assert abs(loss(Q) / loss(g["Wq"]) - 1) < 0.02

@@ -4,7 +4,7 @@ R=${1:-r1}
 mkdir -p gpurun_out
 echo "=== launch list (bench, 2 layers): our kernels only, warm-up skipped"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none \
-  -k regex:"w4a8_gemm|act_quant_i8_kernel|hadk_tc" -s 48 -c 16 --csv \
+  -k regex:"w4a8_gemm|act_quant_i8_kernel|hadk_tc|fwht|rmsn" -s 48 -c 16 --csv \
   --log-file gpurun_out/launches_${R}.csv python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_${R}.log 2>&1
 tail -1 gpurun_out/launches_${R}.log | cut -c1-200
 echo "=== full: gemm (the 4 shapes of the bench step at M=16384)"
@@ -23,8 +23,8 @@ for K, N in ((4096, 12288), (4096, 4096), (4096, 22016), (11008, 4096)):  # q|k|
     torch.cuda.synchronize()
 PY
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:w4a8_gemm -f -o gpurun_out/prof_gemm_${R} python /tmp/gemm_shapes.py > gpurun_out/ncu_gemm_${R}.log 2>&1
-echo "=== full: hadamard tc + quant + minmax + fwht"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"hadk_tc2_kernel|act_quant_i8_kernel|minmax_tensor_kernel|fwht_cta_kernel" -c 12 -f -o gpurun_out/prof_mem_${R} python tools/profile_target.py all 16384 > gpurun_out/ncu_mem_${R}.log 2>&1
+echo "=== full: hadamard (tc3 K=172, tc2 K=28, mma.sync pow2) + quant + minmax + rmsn + gptq hessian"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"hadk_tc|act_quant_i8_kernel|minmax_tensor_kernel|fwht_|rmsn_quant|hessian_kernel" -c 24 -f -o gpurun_out/prof_mem_${R} python tools/profile_target.py all 16384 > gpurun_out/ncu_mem_${R}.log 2>&1
 tail -2 gpurun_out/ncu_mem_${R}.log
 echo "=== microbench (all)"
 timeout 900 python tools/microbench.py --json gpurun_out/microbench_${R}.json > gpurun_out/microbench_${R}.log 2>&1

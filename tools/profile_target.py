@@ -1,5 +1,5 @@
 """Run each hot kernel a few times at the headline shapes (ncu target).
-python tools/profile_target.py [gemm|quant|had|had172|minmax|all] [M]"""
+python tools/profile_target.py [gemm|quant|had|had172|had28|minmax|rmsn|hessian|all] [M]"""
 import os
 import sys
 
@@ -41,5 +41,21 @@ if which in ("had172", "all"):
     hk = hu.hadK_device(172, "cuda")
     for _ in range(reps):
         ops.hadamard(x, had_k=172, hadk=hk, n=11008, scales=scales, modality=mod, want_codes=True, want_f16=False)
+if which in ("had28", "all"):  # InternVL2-8B feed_forward.w2: 14336 = 28 x 512 (hadk_tc2_kernel)
+    x = (torch.randn(M, 14336, device="cuda") * 3).half()
+    hk = hu.hadK_device(28, "cuda")
+    for _ in range(reps):
+        ops.hadamard(x, had_k=28, hadk=hk, n=14336, scales=scales, modality=mod, want_codes=True, want_f16=False)
+if which in ("rmsn", "all"):
+    x = (torch.randn(M, 4096, device="cuda") * 3).half()
+    for _ in range(reps):
+        ops.rmsn_quant_i8(x, 4096, 1e-6, scales=scales, modality=mod)
+if which in ("hessian", "all"):  # GPTQ.add_batch on one 2048-token sample, C = 4096 and 11008
+    for C in (4096, 11008):
+        x = (torch.randn(2048, C, device="cuda") * 3).half()
+        H = torch.zeros(C, C, device="cuda")
+        for i in range(reps):
+            ops.gptq_hessian_update(x, H, i, 1)
+        del H
 torch.cuda.synchronize()
 print("done", which, M)
