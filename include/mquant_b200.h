@@ -202,6 +202,27 @@ int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4, const floa
                     const void* w0, void* out, int64_t ldo, int64_t M, int64_t N, int64_t K,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- (f-3) gated MLP: a1 * silu(a2) as the epilogue of the w1 | w2 GEMM ---------------------- */
+
+/* QWenMLP.forward (model/modeling_qwen_opt.py:382-386): a1 = w1(x), a2 = w2(x), a1 * F.silu(a2), with
+ * the two Linears as ONE W4A8 GEMM whose packed weight holds the rows interleaved in blocks of 128:
+ * packed rows 256 b .. 256 b + 127 = channels 128 b .. of w1, rows 256 b + 128 .. = the same channels
+ * of w2 (s_w and bias in the same order; N2 = 2 F, F % 128 == 0).
+ *   out[m, f] = fp16( fp16(a1[m, f]) * fp16( silu( fp16(a2[m, f]) ) ) ),  silu(x) = x / (1 + exp(-x)) in fp32
+ * (the reference's three fp16 rounding points; a1 / a2 = the mq_w4a8_gemm epilogue).  out: [M, F]
+ * fp16, row stride ldo.  Shapes the 256 x 256 kernel serves (mq_w4a8_gemm_plan == 4) never touch
+ * tmp; the others run the plain GEMM into tmp ([M, N2] fp16, required then) followed by
+ * mq_silu_mul_interleaved_f16 -- same bits either way. */
+int mq_w4a8_gemm_gated_ws(const int8_t* qa, int64_t lda, const uint8_t* w4, const float* s_a,
+                          int s_a_per_row, const float* s_w, const void* bias, void* out, int64_t ldo,
+                          int64_t M, int64_t N2, int64_t K, void* tmp, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* out[m, f] = in[m, 256 (f / 128) + f % 128] * silu(in[m, 256 (f / 128) + 128 + f % 128]), fp16,
+ * the rounding points above; in: [M, 2 F] (row stride ldi), out: [M, F]. */
+int mq_silu_mul_interleaved_f16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M,
+                                int64_t F, void* stream);
+
 /* ---- (f-2) GPTQ acceleration --------------------------------------------------------------- */
 
 /* GPTQ.add_batch (fake_quant/gptq/gptq_utils.py:182-195): H = alpha * H + beta * X^T X with

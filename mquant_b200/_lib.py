@@ -30,6 +30,8 @@ SIGNATURES = {
     "mq_act_quant_i8": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i, _i, _u, _p]),
     "mq_act_fake_quant_f16": (_i, [_p, _i64, _p, _i64, _p, _p, _i, _i, _i64, _i, _p]),
     "mq_rmsn_quant_i8": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i64, _i, _i, C.c_float, C.c_float, _p]),
+    "mq_w4a8_gemm_gated_ws": (_i, [_p, _i64, _p, _p, _i, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, C.c_size_t, _p]),
+    "mq_silu_mul_interleaved_f16": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "mq_gptq_hessian_update": (_i, [_p, _i64, _i64, _i, _p, C.c_float, C.c_float, _p]),
     "mq_gptq_block_f32": (_i, [_p, _i64, _p, _i64, _p, C.c_float, _p, _p, _p, _i, _i, _p]),
     "mq_act_quant_i8_dynamic": (_i, [_p, _i64, _p, _p, _i64, _i, _i, C.c_float, _p]),

@@ -47,6 +47,23 @@ unsigned probe_mask();
 static inline unsigned probe_mask() { return 0u; }
 #endif
 
+// F.silu in fp32 with torch's CUDA expression (ATen ActivationSiluKernel.cu: x / (1 + exp(-x)), expf
+// and an IEEE division), rounded to fp16 like the fp16 tensor F.silu returns
+__device__ __forceinline__ float silu_f32(float x) { return __fdiv_rn(x, __fadd_rn(1.0f, expf(-x))); }
+// 8 x (a1 * silu(a2)) on fp16 values: silu -> fp16 (rounding point), product -> fp16 (rounding point)
+__device__ __forceinline__ uint4 silu_mul8(const uint4& a1, const uint4& a2) {
+  uint4 r;
+  const __half2* h1 = reinterpret_cast<const __half2*>(&a1);
+  const __half2* h2 = reinterpret_cast<const __half2*>(&a2);
+  __half2* o = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 g = __half22float2(h2[i]);
+    o[i] = __hmul2(h1[i], __floats2half2_rn(silu_f32(g.x), silu_f32(g.y)));
+  }
+  return r;
+}
+
 __device__ __forceinline__ void unpack_store(uint32_t brow, int rsw, int j, const uint4& p) {
   // low nibbles -> k = 32j .. 32j+15 (16-byte chunk 2j), high nibbles -> chunk 2j+1; values x16
   const uint32_t lo0 = (p.x << 4) & 0xF0F0F0F0u, lo1 = (p.y << 4) & 0xF0F0F0F0u;
@@ -64,7 +81,9 @@ __device__ __forceinline__ void unpack_store(uint32_t brow, int rsw, int j, cons
 int launch_w4a8_gemm_v2(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st);
 // mq_gemm_w4a8_v4.cu: 256 x 256 tile per CTA, one converted weight k-block shared by two M halves
 // (tmap_out: fp16 output, 32 x 32 boxes, SWIZZLE_64B -- the epilogue stores through TMA)
-int launch_w4a8_gemm_v4(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out, const Params& p, cudaStream_t st);
+// gated: interleaved w1 | w2 rows, output [M, N / 2] = a1 * silu(a2) (tmap_out describes that tensor)
+int launch_w4a8_gemm_v4(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out, const Params& p, cudaStream_t st,
+                        bool gated = false);
 // mq_gemm_w4a8_sk.cu: split-K flavour of the 128 x 256 kernel for mid-sized M (int32 partial sums in
 // a caller-provided self-cleaning workspace); splitk_factor() == 1 means "not worth it"
 int splitk_factor(int64_t M, int64_t N, int64_t K);

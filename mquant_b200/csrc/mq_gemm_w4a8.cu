@@ -72,10 +72,10 @@ extern "C" int mq_w4a8_gemm(const int8_t* qa, int64_t lda, const uint8_t* w4, co
   return mq_w4a8_gemm_ws(qa, lda, w4, s_a, s_a_per_row, s_w, bias, x0, w0, out, ldo, M, N, K, nullptr, 0, stream);
 }
 
-extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4, const float* s_a, int s_a_per_row,
-                               const float* s_w, const void* bias, const void* x0, const void* w0, void* out,
-                               int64_t ldo, int64_t M, int64_t N, int64_t K, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+static int gemm_impl(const int8_t* qa, int64_t lda, const uint8_t* w4, const float* s_a, int s_a_per_row,
+                     const float* s_w, const void* bias, const void* x0, const void* w0, void* out, int64_t ldo,
+                     int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes, void* stream,
+                     bool gated) {
   using namespace mq;
   using namespace mq::gemm;
   if (M == 0) return MQ_OK;  // empty batch: nothing to do (its tensors have null data pointers)
@@ -83,8 +83,8 @@ extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4,
   MQ_REQUIRE(M >= 0 && N > 0 && K > 0, "mq_w4a8_gemm: bad shape (M=%lld N=%lld K=%lld)", (long long)M,
              (long long)N, (long long)K);
   MQ_REQUIRE(K % BK == 0, "mq_w4a8_gemm: K=%lld must be a multiple of %d (zero-pad the codes)", (long long)K, BK);
-  MQ_REQUIRE(N % 8 == 0 && ldo % 8 == 0 && ldo >= N, "mq_w4a8_gemm: N and ldo must be multiples of 8 (N=%lld ldo=%lld)",
-             (long long)N, (long long)ldo);
+  MQ_REQUIRE(N % 8 == 0 && ldo % 8 == 0 && ldo >= (gated ? N / 2 : N),
+             "mq_w4a8_gemm: N and ldo must be multiples of 8 (N=%lld ldo=%lld)", (long long)N, (long long)ldo);
   MQ_REQUIRE(lda % 16 == 0 && lda >= K, "mq_w4a8_gemm: lda=%lld must be a multiple of 16 and >= K", (long long)lda);
   MQ_REQUIRE(aligned16(qa) && aligned16(w4) && aligned16(out), "mq_w4a8_gemm: pointers must be 16-byte aligned");
   MQ_REQUIRE((x0 == nullptr) == (w0 == nullptr), "mq_w4a8_gemm: x0 and w0 go together");
@@ -122,6 +122,7 @@ extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4,
   const int forced = g_force_kernel.load(std::memory_order_relaxed);
   if (forced == 3 || forced == 4) kernel = forced;
   if (p.dbg != 0 && kernel < 3) kernel = 3;  // the probes live in the persistent kernels
+  if (gated) kernel = 4;                     // (the caller has checked that this is the planned kernel)
   cudaStream_t st = (cudaStream_t)stream;
   if (kernel == 1) {
     const int rc = launch_w4a8_gemv(qa, lda, p, workspace, st);
@@ -138,7 +139,7 @@ extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4,
   if (kernel == 4) {
     // the 256 x 256 kernel writes its output with TMA: 32 x 32 fp16 boxes out of swizzled staging
     CUtensorMap tmap_out;
-    const cuuint64_t odim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint64_t odim[2] = {(cuuint64_t)(gated ? N / 2 : N), (cuuint64_t)M};
     const cuuint64_t ostride[1] = {(cuuint64_t)ldo * 2};
     const cuuint32_t obox[2] = {32, 32};
     const CUresult cro = encode(&tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out, odim, ostride, obox, estride,
@@ -148,7 +149,7 @@ extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4,
       set_error("mq_w4a8_gemm: cuTensorMapEncodeTiled (output) failed with CUresult %d", (int)cro);
       return MQ_ERR_CUDA;
     }
-    const int rc = launch_w4a8_gemm_v4(tmap, tmap_out, p, st);
+    const int rc = launch_w4a8_gemm_v4(tmap, tmap_out, p, st, gated);
     if (rc != MQ_OK) return rc;
     MQ_LAUNCH_CHECK("w4a8_gemm_v4_kernel");
     return MQ_OK;
@@ -157,6 +158,75 @@ extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4,
   if (rc != MQ_OK) return rc;
   MQ_LAUNCH_CHECK("w4a8_gemm_v2_kernel");
   return MQ_OK;
+}
+
+extern "C" int mq_w4a8_gemm_ws(const int8_t* qa, int64_t lda, const uint8_t* w4, const float* s_a, int s_a_per_row,
+                               const float* s_w, const void* bias, const void* x0, const void* w0, void* out,
+                               int64_t ldo, int64_t M, int64_t N, int64_t K, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  return gemm_impl(qa, lda, w4, s_a, s_a_per_row, s_w, bias, x0, w0, out, ldo, M, N, K, workspace, workspace_bytes, stream,
+                   false);
+}
+
+// ---- gated MLP: a1 * silu(a2) in the epilogue -------------------------------------
+namespace mq {
+namespace gemm {
+
+// out[m, f] = in[m, 256 (f / 128) + f % 128] * silu(in[m, 256 (f / 128) + 128 + f % 128]): the gate on an
+// un-gated GEMM output over interleaved weights -- same arithmetic as the fused epilogue (silu_mul8)
+__global__ void __launch_bounds__(256) silu_mul_interleaved_kernel(const __half* __restrict__ in, int64_t ldi,
+                                                                  __half* __restrict__ out, int64_t ldo, int64_t M, int F) {
+  const int chunks = F / 8;  // 16-byte chunks per output row
+  const int64_t total = M * chunks;
+  for (int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; id < total; id += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = id / chunks;
+    const int f = (int)(id - m * chunks) * 8;
+    const __half* src = in + m * ldi + (f >> 7) * 256 + (f & 127);
+    const uint4 a1 = *reinterpret_cast<const uint4*>(src), a2 = *reinterpret_cast<const uint4*>(src + 128);
+    *reinterpret_cast<uint4*>(out + m * ldo + f) = silu_mul8(a1, a2);
+  }
+}
+
+}  // namespace gemm
+}  // namespace mq
+
+extern "C" int mq_silu_mul_interleaved_f16(const void* in, int64_t ldi, void* out, int64_t ldo, int64_t M, int64_t F,
+                                           void* stream) {
+  using namespace mq;
+  if (M == 0) return MQ_OK;
+  MQ_REQUIRE(in && out, "mq_silu_mul_interleaved_f16: null pointer");
+  MQ_REQUIRE(M > 0 && F > 0 && F % 128 == 0 && ldi % 8 == 0 && ldo % 8 == 0 && ldi >= 2 * F && ldo >= F && F < (1ll << 30),
+             "mq_silu_mul_interleaved_f16: bad shape (F=%lld must be a multiple of 128)", (long long)F);
+  MQ_REQUIRE(aligned16(in) && aligned16(out), "mq_silu_mul_interleaved_f16: pointers must be 16-byte aligned");
+  const int64_t total = M * (F / 8);
+  const int64_t want = (total + 255) / 256, cap = (int64_t)num_sms() * 16;
+  gemm::silu_mul_interleaved_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)in, ldi, (__half*)out, ldo, M, (int)F);
+  MQ_LAUNCH_CHECK("mq_silu_mul_interleaved_f16");
+  return MQ_OK;
+}
+
+extern "C" int mq_w4a8_gemm_gated_ws(const int8_t* qa, int64_t lda, const uint8_t* w4, const float* s_a, int s_a_per_row,
+                                     const float* s_w, const void* bias, void* out, int64_t ldo, int64_t M, int64_t N2,
+                                     int64_t K, void* tmp, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace mq;
+  using namespace mq::gemm;
+  if (M == 0) return MQ_OK;
+  MQ_REQUIRE(N2 > 0 && N2 % 256 == 0, "mq_w4a8_gemm_gated: N2=%lld must be a multiple of 256 (128 channels of w1, 128 of w2)",
+             (long long)N2);
+  MQ_REQUIRE(K > 0 && K % BK == 0, "mq_w4a8_gemm_gated: K=%lld must be a multiple of %d", (long long)K, BK);
+  int kernel = plan_kernel(M, N2, K, workspace != nullptr ? workspace_bytes : 0);
+  const int forced = g_force_kernel.load(std::memory_order_relaxed);
+  if (forced == 3 || forced == 4) kernel = forced;
+  if (kernel == 4)
+    return gemm_impl(qa, lda, w4, s_a, s_a_per_row, s_w, bias, nullptr, nullptr, out, ldo, M, N2, K, workspace,
+                     workspace_bytes, stream, true);
+  // shapes the 256 x 256 kernel does not serve: the plain GEMM into tmp, then the same gate arithmetic
+  MQ_REQUIRE(tmp != nullptr, "mq_w4a8_gemm_gated: M=%lld runs the two-step path and needs tmp [M, N2] fp16", (long long)M);
+  const int rc = gemm_impl(qa, lda, w4, s_a, s_a_per_row, s_w, bias, nullptr, nullptr, tmp, N2, M, N2, K, workspace,
+                           workspace_bytes, stream, false);
+  if (rc != MQ_OK) return rc;
+  return mq_silu_mul_interleaved_f16(tmp, N2, out, ldo, M, N2 / 2, stream);
 }
 
 extern "C" int mq_debug_force_gemm_kernel(int kernel) {

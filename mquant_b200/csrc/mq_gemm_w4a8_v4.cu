@@ -80,7 +80,14 @@ constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >
 // HAS_R1 / HAS_BIAS are compile-time: one straight-line epilogue per variant (with run-time flags
 // the compiler emitted four code copies per 8-column group and the epilogue warps, two per
 // scheduler, stalled on instruction fetch for ~20 % of their active time -- profiles/README.md).
-template <bool HAS_R1, bool HAS_BIAS>
+//
+// GATED (model/modeling_qwen_opt.py:382-386): the weight rows are interleaved in
+// blocks of 128 -- columns 0..127 of a tile are channels f0..f0+127 of w1, columns 128..255 the same
+// channels of w2 -- and the epilogue writes  fp16(a1) * fp16(silu(fp16(a2)))  to a [M, N/2] output:
+// the reference's three fp16 rounding points (both Linear outputs, F.silu's result, the product),
+// silu in fp32 with torch's expression x / (1 + exp(-x)).  A thread needs a1 and a2 of the same
+// channel, so a warp owns 64 gated channels (two 32-column blocks of BOTH column halves).
+template <bool HAS_R1, bool HAS_BIAS, bool GATED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_out,
                     const Params p) {
@@ -347,7 +354,7 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * BN + col0);
         uint32_t va[32], vb[32];
-        tmem_ld32_nowait(taddr, va);
+        if constexpr (!GATED) tmem_ld32_nowait(taddr, va);
         const uint64_t sa2p = f2_pack(sa, sa), x0v2p = f2_pack(x0v, x0v);
         auto process = [&](const uint32_t (&v)[32], int cc) {
           const int colb = col0 + cc * 32;
@@ -410,6 +417,59 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             bulk_commit_group();
           }
         };
+        if constexpr (GATED) {
+          // 16 gated channels per step: a1 from columns c .. c+15, a2 from 128 + c ..; the loads of the
+          // next step are in flight while this one is computed; two steps fill one 32 x 32 output box
+          (void)va;
+          const uint32_t tg = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * BN + chalf * 64);
+          uint32_t g1[2][16], g2[2][16];
+          tmem_ld16_nowait(tg, g1[0]);
+          tmem_ld16_nowait(tg + 128, g2[0]);
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            tmem_wait_ld();
+            if (s4 < 3) {
+              tmem_ld16_nowait(tg + (s4 + 1) * 16, g1[(s4 + 1) & 1]);
+              tmem_ld16_nowait(tg + 128 + (s4 + 1) * 16, g2[(s4 + 1) & 1]);
+            }
+            const uint32_t stg = stg0 + sbuf;
+            if ((s4 & 1) == 0) {
+              if (L::STG_BUFS == 2) {
+                if (lane == 0) bulk_wait_read_le1();
+              } else {
+                if (lane == 0) bulk_wait_read_all();
+              }
+              __syncwarp();
+            }
+            const int c1 = chalf * 64 + s4 * 16;  // column of a1 inside the tile; a2 sits 128 further
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              float y1[8], y2[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int col = c1 + g * 8 + e;
+                y1[e] = __fmul_rn((float)(int)g1[s4 & 1][g * 8 + e], __fmul_rn(sa, ps[col]));
+                y2[e] = __fmul_rn((float)(int)g2[s4 & 1][g * 8 + e], __fmul_rn(sa, ps[128 + col]));
+                if (has_bias) {
+                  y1[e] = __fadd_rn(y1[e], __half2float(ps_bias[col]));
+                  y2[e] = __fadd_rn(y2[e], __half2float(ps_bias[128 + col]));
+                }
+              }
+              const uint4 hv = silu_mul8(pack8_f16(y1), pack8_f16(y2));
+              const uint32_t dst = stg + lane * 64 + ((uint32_t)(((s4 & 1) * 2 + g) ^ ((lane >> 1) & 3)) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(hv.x), "r"(hv.y), "r"(hv.z), "r"(hv.w));
+            }
+            if (s4 & 1) {
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmap_out, stg, nb * (BN / 2) + chalf * 64 + (s4 >> 1) * 32, m_warp0);
+                bulk_commit_group();
+              }
+              if (L::STG_BUFS == 2) sbuf ^= STG_BYTES;
+            }
+          }
+        } else
 #pragma unroll 1
         for (int cc = 0; cc < (BN / 2) / 32; cc += 2) {
           tmem_wait_ld();
@@ -434,28 +494,34 @@ w4a8_gemm_v4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
 }  // namespace v4
 
-template <bool HAS_R1, bool HAS_BIAS>
+template <bool HAS_R1, bool HAS_BIAS, bool GATED>
 static int launch_variant(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out, const Params& p, int grid,
                           cudaStream_t st) {
   using namespace v4;
-  auto* kern = w4a8_gemm_v4_kernel<HAS_R1, HAS_BIAS>;
+  auto* kern = w4a8_gemm_v4_kernel<HAS_R1, HAS_BIAS, GATED>;
   constexpr int SM_ALLOC = Lay<HAS_R1, HAS_BIAS>::SM_ALLOC;
   MQ_DYN_SMEM(kern, SM_ALLOC);
   kern<<<grid, NUM_THREADS, SM_ALLOC, st>>>(tmap_a, tmap_out, p);
   return MQ_OK;
 }
 
-int launch_w4a8_gemm_v4(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out, const Params& p_in, cudaStream_t st) {
+int launch_w4a8_gemm_v4(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out, const Params& p_in, cudaStream_t st,
+                        bool gated) {
   using namespace v4;
   Params p = p_in;
   p.m_tiles = (p.M + BM - 1) / BM;
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   const bool r1 = p.x0 != nullptr, bias = p.bias != nullptr;
-  if (r1) return bias ? launch_variant<true, true>(tmap_a, tmap_out, p, grid, st)
-                      : launch_variant<true, false>(tmap_a, tmap_out, p, grid, st);
-  return bias ? launch_variant<false, true>(tmap_a, tmap_out, p, grid, st)
-              : launch_variant<false, false>(tmap_a, tmap_out, p, grid, st);
+  if (gated) {
+    if (r1) return MQ_ERR_UNSUPPORTED;
+    return bias ? launch_variant<false, true, true>(tmap_a, tmap_out, p, grid, st)
+                : launch_variant<false, false, true>(tmap_a, tmap_out, p, grid, st);
+  }
+  if (r1) return bias ? launch_variant<true, true, false>(tmap_a, tmap_out, p, grid, st)
+                      : launch_variant<true, false, false>(tmap_a, tmap_out, p, grid, st);
+  return bias ? launch_variant<false, true, false>(tmap_a, tmap_out, p, grid, st)
+              : launch_variant<false, false, false>(tmap_a, tmap_out, p, grid, st);
 }
 
 }  // namespace gemm

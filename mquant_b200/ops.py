@@ -349,6 +349,53 @@ def w4a8_gemm(q, w4, s_a, s_w, N, bias=None, x0=None, w0=None, out=None, simt=Fa
     return out
 
 
+def interleave_gated(v1, v2):
+    """Rows (or entries) of w1 / w2 in the order of the gated GEMM: blocks of 128 of v1 and v2 alternate
+    (mq_w4a8_gemm_gated_ws).  v1, v2: [F, ...] with F % 128 == 0."""
+    F = v1.shape[0]
+    if F % 128 != 0 or v2.shape != v1.shape:
+        raise _lib.MQuantLibraryError("interleave_gated: two equal shapes with a multiple of 128 rows")
+    rest = v1.shape[1:]
+    return torch.stack((v1.reshape(F // 128, 128, *rest), v2.reshape(F // 128, 128, *rest)), dim=1).reshape(2 * F, *rest)
+
+
+@_on_device
+def silu_mul_interleaved(a, F, out=None):
+    """mq_silu_mul_interleaved_f16: a = [M, 2F] output of a GEMM over interleave_gated weights -> [M, F]."""
+    _need_cuda(a)
+    assert a.dtype == torch.float16 and a.dim() == 2 and a.shape[1] == 2 * F and a.stride(1) == 1
+    M = a.shape[0]
+    if out is None:
+        out = torch.empty((M, F), dtype=torch.float16, device=a.device)
+    check(lib().mq_silu_mul_interleaved_f16(_ptr(a), _ld(a), _ptr(out), _ld(out), M, F, _stream()),
+          "mq_silu_mul_interleaved_f16")
+    return out
+
+
+@_on_device
+def w4a8_gemm_gated(q, w4, s_a, s_w, F, bias=None, out=None):
+    """mq_w4a8_gemm_gated_ws: w4 / s_w / bias over interleave_gated(w1, w2) rows (N2 = 2F) -> fp16 [M, F] =
+    a1 * silu(a2) (QWenMLP.forward, model/modeling_qwen_opt.py:382-386)."""
+    _need_cuda(q, w4, s_a, s_w, bias)
+    assert q.dtype == torch.int8 and q.dim() == 2 and q.stride(1) == 1
+    M, K = q.shape
+    if s_a.numel() not in (1, M):
+        raise _lib.MQuantLibraryError("w4a8_gemm_gated: s_a must have 1 or M elements")
+    if out is None:
+        out = torch.empty((M, F), dtype=torch.float16, device=q.device)
+    ws = _gemm_workspace(q.device, M, 2 * F, K)
+    nws = 0 if ws is None else ws.numel()
+    tmp = None
+    if M > 0 and lib().mq_w4a8_gemm_plan(M, 2 * F, K, nws) != 4:
+        tmp = torch.empty((M, 2 * F), dtype=torch.float16, device=q.device)
+    lda = q.stride(0) if M > 1 else max(K, q.stride(0))
+    ldo = out.stride(0) if M > 1 else max(F, out.stride(0))
+    check(lib().mq_w4a8_gemm_gated_ws(_ptr(q), lda, _ptr(w4), _ptr(s_a), int(s_a.numel() == M), _ptr(s_w), _ptr(bias),
+                                      _ptr(out), ldo, M, 2 * F, K, _ptr(tmp), _ptr(ws), nws, _stream()),
+          "mq_w4a8_gemm_gated")
+    return out
+
+
 _gemm_ws = {}
 
 

@@ -869,6 +869,102 @@ def fuse_siblings(wrappers):
     return g
 
 
+class _GatedPair:
+    """The two input projections of a gated MLP as ONE W4A8 GEMM whose epilogue applies the gate
+    (QWenMLP.forward, model/modeling_qwen_opt.py:382-386: ``a1 * F.silu(a2)``):
+    ``value`` = the wrapper of a1 (Qwen-VL ``w1``, Llama-style ``up_proj``, InternLM2 ``w3``), ``gate`` =
+    the wrapper whose output goes through silu (``w2`` / ``gate_proj`` / ``w1``).  The packed weight
+    interleaves their rows in blocks of 128 (ops.interleave_gated); the [M, 2F] intermediate is never
+    written for batches the 256 x 256 kernel serves.  Same fp16 rounding points as the reference."""
+
+    def __init__(self, value, gate):
+        pv, pg = value._packed, gate._packed
+        self.value, self.gate = value, gate
+        self.F, self.Kp = pv["N"], pv["Kp"]
+        codes = ops.interleave_gated(ops.unpack_w4(pv["w4"], self.F, self.Kp), ops.unpack_w4(pg["w4"], self.F, self.Kp))
+        self.w4 = ops.pack_w4(codes)
+        self.s_w = ops.interleave_gated(pv["s_w"].reshape(-1), pg["s_w"].reshape(-1)).contiguous()
+        self.bias = None
+        if pv["bias"] is not None or pg["bias"] is not None:
+            z = torch.zeros(self.F, dtype=torch.float16, device=self.w4.device)  # (+0.0 leaves every fp32 sum unchanged)
+            self.bias = ops.interleave_gated(pv["bias"] if pv["bias"] is not None else z,
+                                             pg["bias"] if pg["bias"] is not None else z).contiguous()
+
+    @torch.no_grad()
+    def forward(self, x):
+        w = self.value
+        qz = w.quantizer.quantizer
+        x2 = x.reshape(-1, x.shape[-1])
+        out_dtype = x2.dtype
+        if x2.dtype == torch.bfloat16:
+            x2 = x2.clamp(-65504.0, 65504.0).to(torch.float16)
+        scales = qz.device_scales(x.device)
+        modality = w.quantizer._modality(x) if qz.scale_visual is not None else None
+        pre = _prequant_of(x, scales, self.Kp, modality)
+        if pre is not None:
+            q, srow = pre
+        else:
+            q, srow, _ = ops.act_quant_i8(x2, scales, modality, n_out=self.Kp, split=False,
+                                          want_row_scales=modality is not None)
+        s_a = srow if modality is not None else scales[0:1]
+        y = ops.w4a8_gemm_gated(q, self.w4, s_a, self.s_w, self.F, bias=self.bias)
+        if out_dtype != torch.float16:
+            y = y.to(out_dtype)
+        return y.reshape(*x.shape[:-1], self.F)
+
+    __call__ = forward
+
+
+def fuse_gated_pair(value, gate):
+    """-> _GatedPair, or None (wrappers untouched) unless the fusion is exact: both frozen, fp16
+    Linears of the same shape with F % 128 == 0, identical static activation scales, no online
+    rotation / split / output quantiser."""
+    f = value
+    for w in (value, gate):
+        if not (isinstance(w, ActQuantWrapper) and w.real_quant and w._packed is not None):
+            return None
+        if w.online_full_had or w.online_partial_had or w.split or w.out_quantizer.bits < 16:
+            return None
+        if w._packed["Kp"] != f._packed["Kp"] or w._packed["K"] != f._packed["K"] or w._packed["N"] != f._packed["N"]:
+            return None
+        if w.module.weight.dtype != torch.float16:  # (bf16 models round a1 / silu / the product to bf16)
+            return None
+        a, b = w.quantizer.quantizer, f.quantizer.quantizer
+        if w.quantizer.msq != f.quantizer.msq or not torch.equal(a.scale.float().cpu(), b.scale.float().cpu()):
+            return None
+        if (a.scale_visual is None) != (b.scale_visual is None):
+            return None
+        if a.scale_visual is not None and not torch.equal(a.scale_visual.float().cpu(), b.scale_visual.float().cpu()):
+            return None
+    if f._packed["N"] % 128 != 0:
+        return None
+    return _GatedPair(value, gate)
+
+
+_GATED_MLP_NAMES = (("w1", "w2", "c_proj"),             # Qwen-VL: c_proj(w1(x) * silu(w2(x)))  (modeling_qwen_opt.py:382-386)
+                    ("up_proj", "gate_proj", "down_proj"),  # Qwen2-VL / MiniCPM-V (Llama style)
+                    ("w3", "w1", "w2"))                  # InternLM2 (InternVL2): w2(silu(w1(x)) * w3(x))
+
+
+def fuse_gated_mlp(mlp):
+    """Route ``mlp.forward`` through one gated GEMM + the down projection.  Recognises the three
+    naming schemes of the supported models; the activation must be SiLU.  Returns the _GatedPair or
+    None when the module was left alone."""
+    for value, gate, down in _GATED_MLP_NAMES:
+        if all(isinstance(getattr(mlp, n, None), ActQuantWrapper) for n in (value, gate, down)):
+            act = getattr(mlp, "act_fn", None)
+            if act is not None and not isinstance(act, torch.nn.SiLU) and getattr(act, "__name__", "") != "silu":
+                return None
+            pair = fuse_gated_pair(getattr(mlp, value), getattr(mlp, gate))
+            if pair is None:
+                return None
+            down_w = getattr(mlp, down)
+            mlp._mq_gated = pair
+            mlp.forward = lambda hidden_states, _p=pair, _d=down_w: _d(_p(hidden_states))
+            return pair
+    return None
+
+
 @torch.no_grad()
 def model_freeze(model, args=None, weight_quantizers=None):
     """New: switch every calibrated Linear wrapper to the real W4A8 path.  ``weight_quantizers`` is

@@ -515,6 +515,16 @@ def qlinear_int(codes_a, s_a, codes_w, s_w, bias=None, x0=None, w0=None):
 # ----------------------------------------------------------------------------------
 
 
+def silu_mul(a1, a2):
+    """a1 * F.silu(a2) on fp16 tensors (QWenMLP.forward, model/modeling_qwen_opt.py:385): silu in fp32
+    (x / (1 + exp(-x))), rounded to fp16 (the tensor F.silu returns), product rounded to fp16."""
+    a1, a2 = np.asarray(a1, F16), np.asarray(a2, F16)
+    x = a2.astype(F32)
+    with np.errstate(over="ignore"):
+        s = (x / (F32(1) + np.exp(-x, dtype=F32))).astype(F32).astype(F16)
+    return (a1.astype(F32) * s.astype(F32)).astype(F16)
+
+
 def gptq_hessian(H, nsamples, x, batch):
     """GPTQ.add_batch (fake_quant/gptq/gptq_utils.py:182-195) in float64 (the check value for the
     fp32 tensor-core sum): returns (H', nsamples')."""

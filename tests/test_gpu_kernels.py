@@ -837,3 +837,73 @@ def test_gptq_fasterquant_matches_reference_golden(ops, golden):
             Err1[:, i] = err1
         W[:, i2:] -= Err1.matmul(Hinv[i1:i2, i2:])
     assert torch.equal(Qe, layer.weight.data)
+
+
+# ------------------------------------------------------------------------------- gated MLP (f-3)
+def _ulp16(a, b):
+    return np.abs(np.asarray(a, np.float16).view(np.int16).astype(np.int32) - np.asarray(b, np.float16).view(np.int16).astype(np.int32))
+
+
+@pytest.mark.parametrize("kernel,M,F,K,per_row,bias", [
+    ("v4", 300, 256, 256, True, False),
+    ("v4", 1000, 1280, 512, True, True),
+    ("v4", 257, 128, 1152, False, True),
+    ("default", 40, 256, 256, True, True),     # split-K / 128 x 256 kernels: GEMM into tmp, then the gate kernel
+    ("default", 3, 384, 512, False, False),    # decode kernel
+])
+def test_gemm_gated_matches_oracle(ops, force, kernel, M, F, K, per_row, bias):
+    """mq_w4a8_gemm_gated_ws (a1 * silu(a2) in the epilogue of the w1 | w2 GEMM over interleaved rows,
+    QWenMLP.forward model/modeling_qwen_opt.py:382-386) vs the oracle: a1 / a2 = the exact integer
+    GEMM + epilogue, then oracle.silu_mul (pinned to the reference's MLP in test_oracle_golden.py).
+    expf on the device and numpy's exp differ by an fp32 ulp on some inputs: <= 2 fp16 ulp on < 1e-3 of
+    the entries; against torch's own CUDA silu (the reference's operator on a GPU) bit for bit."""
+    rng = np.random.default_rng(M * 3 + F + K)
+    c1 = gemm_case(rng, M, F, K, per_row, bias, False)
+    c2 = gemm_case(rng, M, F, K, per_row, bias, False)
+    qa, s_a = c1[0], c1[2]
+    a1 = oracle_gemm((qa, c1[1], s_a, c1[3], c1[4], None, None))
+    a2 = oracle_gemm((qa, c2[1], s_a, c2[3], c2[4], None, None))
+    want = O.silu_mul(a1, a2)
+    w4 = ops.pack_w4(ops.interleave_gated(dev(c1[1]), dev(c2[1])))
+    s_w = ops.interleave_gated(dev(c1[3]), dev(c2[3]))
+    b = ops.interleave_gated(dev(c1[4]), dev(c2[4])) if bias else None
+    if kernel != "default":
+        force.gemm(kernel)
+    got = ops.w4a8_gemm_gated(dev(qa), w4, dev(s_a), s_w, F, bias=b)
+    torch.cuda.synchronize()
+    d = _ulp16(host(got), want)
+    assert d.max() <= 2 and (d > 0).mean() < 1e-3, (int(d.max()), float((d > 0).mean()))
+    ref = dev(a1) * torch.nn.functional.silu(dev(a2))
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    # the plain GEMM over the same interleaved weights + the stand-alone gate kernel: same bits
+    full = ops.w4a8_gemm(dev(qa), w4, dev(s_a), s_w, 2 * F, bias=b)
+    assert torch.equal(ops.silu_mul_interleaved(full, F), got)
+
+
+def test_gemm_gated_at_benchmark_shape(ops):
+    """Qwen-VL's MLP at the benchmark's batch: M = 16384, K = 4096, F = 11008 through the default
+    dispatcher (the fused 256 x 256 epilogue), against the un-fused chain on the device (plain GEMM,
+    bit-exact vs the integer oracle in test_gemm_default_dispatch_at_benchmark_shapes, then torch's
+    silu and product) bit for bit, and against the oracle on sampled rows."""
+    from mquant_b200._lib import lib
+
+    M, K, F = 16384, 4096, 11008
+    assert lib().mq_w4a8_gemm_plan(M, 2 * F, K, lib().mq_w4a8_gemm_workspace_bytes(M, 2 * F, K)) == 4
+    g = torch.Generator(device="cuda").manual_seed(385)
+    qa = torch.randint(-128, 128, (M, K), dtype=torch.int8, device="cuda", generator=g)
+    cw1 = torch.randint(-8, 8, (F, K), dtype=torch.int8, device="cuda", generator=g)
+    cw2 = torch.randint(-8, 8, (F, K), dtype=torch.int8, device="cuda", generator=g)
+    s_a = torch.rand(M, device="cuda", generator=g) * 0.05 + 0.01
+    sw1 = torch.rand(F, device="cuda", generator=g) * 0.01 + 0.001
+    sw2 = torch.rand(F, device="cuda", generator=g) * 0.01 + 0.001
+    w4 = ops.pack_w4(ops.interleave_gated(cw1, cw2))
+    got = ops.w4a8_gemm_gated(qa, w4, s_a, ops.interleave_gated(sw1, sw2), F)
+    a1 = ops.w4a8_gemm(qa, ops.pack_w4(cw1), s_a, sw1, F)
+    a2 = ops.w4a8_gemm(qa, ops.pack_w4(cw2), s_a, sw2, F)
+    ref = a1 * torch.nn.functional.silu(a2)
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    rows = torch.from_numpy(np.random.default_rng(1).integers(0, M, 96)).cuda()
+    o1 = oracle_gemm((host(qa[rows]), host(cw1), host(s_a[rows]), host(sw1), None, None, None))
+    o2 = oracle_gemm((host(qa[rows]), host(cw2), host(s_a[rows]), host(sw2), None, None, None))
+    d = _ulp16(host(got[rows]), O.silu_mul(o1, o2))
+    assert d.max() <= 2 and (d > 0).mean() < 1e-3

@@ -227,6 +227,50 @@ def test_qwen_block_output_matches_reference(qu, golden):
     assert np.allclose(rn, g["block_y_rownorm"], rtol=5e-3), float(np.abs(rn / g["block_y_rownorm"] - 1).max())
 
 
+@torch.no_grad()
+def test_gated_mlp_matches_reference_block(qu, golden):
+    """QWenMLP.forward (model/modeling_qwen_opt.py:382-386) through fuse_gated_mlp --
+    w1 | w2 as one gated W4A8 GEMM (a1 * silu(a2) in the epilogue), then the Hadamard + c_proj wrapper.
+    (1) bit-identical to the un-fused integer chain w1(x) * silu(w2(x)); (2) the gated tensor and the
+    MLP output agree with what the reference block recorded for mlp.c_proj (its input is a1 * silu(a2)
+    of the reference's fake-quant path) on the fixture's 16 token rows; (3) large batches (the fused
+    256 x 256 epilogue) agree bit for bit with the two-step path."""
+    g = golden("qwen_block")
+    wr, wq_scales = _our_block(qu, g)
+    for name in ("mlp.w1", "mlp.w2", "mlp.c_proj"):
+        wr[name].freeze(wq_scales[name], check=True)
+
+    class MLP(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w1, self.w2, self.c_proj = wr["mlp.w1"], wr["mlp.w2"], wr["mlp.c_proj"]
+
+        def forward(self, h):
+            return self.c_proj(self.w1(h) * torch.nn.functional.silu(self.w2(h)))
+
+    mlp = MLP()
+    x = torch.from_numpy(g["mlp_w1_x"]).cuda()
+    gate_ref = mlp.w1(x) * torch.nn.functional.silu(mlp.w2(x))
+    y_ref = mlp(x)
+    pair = qu.fuse_gated_mlp(mlp)
+    assert pair is not None and pair.F == 11008
+    gated = pair(x)
+    assert torch.equal(gated.view(torch.int16), gate_ref.view(torch.int16))
+    assert torch.equal(mlp(x).view(torch.int16), y_ref.view(torch.int16))
+    cos, err = cos_maxabs(gated.cpu().numpy(), g["mlp_c_proj_x"])
+    assert cos >= 0.9999 and err <= 8 * 2.0 ** -9 * np.abs(g["mlp_c_proj_x"]).max() + 1e-3, (cos, err)
+    cos, err = cos_maxabs(mlp(x).cpu().numpy(), g["mlp_c_proj_y"])
+    assert cos >= 0.999, cos
+    # a prefill-sized batch: the fused epilogue of the 256 x 256 kernel
+    from mquant_b200._lib import lib
+    xb = torch.from_numpy(g["mlp_w1_x"]).cuda().repeat(256, 1)
+    xb = (xb * (1 + 0.05 * torch.randn(xb.shape[0], 1, device="cuda"))).half()
+    assert lib().mq_w4a8_gemm_plan(xb.shape[0], 2 * 11008, 4096, 0) == 4
+    big = pair(xb)
+    two_step = wr["mlp.w1"](xb) * torch.nn.functional.silu(wr["mlp.w2"](xb))
+    assert torch.equal(big.view(torch.int16), two_step.view(torch.int16))
+
+
 @pytest.mark.parametrize("model,had_name,k_in,k_pad,had_k", [
     ("qwen2vl-7b", "mlp_down_proj", 18944, 19968, 156),       # BASELINE config 4: padded down_proj
     ("internvl2-8b", "feed_forward_w2", 14336, 14336, 28),    # BASELINE config 3: 28 x 512

@@ -282,3 +282,16 @@ def test_gptq_oracle_matches_reference(golden):
         return float(np.einsum("ij,jk,ik->", D, g["H"].astype(np.float64), D))
 
     assert abs(loss(Q) / loss(g["Wq"]) - 1) < 0.02
+
+
+def test_silu_mul_oracle_matches_reference_mlp(golden):
+    """oracle.silu_mul vs the reference's QWenMLP.forward (model/modeling_qwen_opt.py:382-386) inside
+    the QWenBlock fixture: inputs = the outputs of the w1 / w2 wrappers, output = what mlp.c_proj was
+    fed (16 token rows x 11008 channels, torch CPU fp16).  fp16 results; exp differs between libms by
+    an fp32 ulp or two, which moves silu's fp16 rounding by one ulp for a few inputs (here a2 = -0.714)
+    and the product by up to two."""
+    g = golden("qwen_block")
+    got = O.silu_mul(g["mlp_w1_y"], g["mlp_w2_y"])
+    want = g["mlp_c_proj_x"]
+    d = np.abs(got.view(np.int16).astype(np.int32) - want.view(np.int16).astype(np.int32))
+    assert d.max() <= 2 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())

@@ -22,10 +22,15 @@ for K, N in ((4096, 12288), (4096, 4096), (4096, 22016), (11008, 4096)):  # q|k|
         ops.w4a8_gemm(q, w4, s_a, s_w, N)
     torch.cuda.synchronize()
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:w4a8_gemm -f -o gpurun_out/prof_gemm_${R} python /tmp/gemm_shapes.py > gpurun_out/ncu_gemm_${R}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:w4a8_gemm -f -o /tmp/prof_gemm_${R} python /tmp/gemm_shapes.py > gpurun_out/ncu_gemm_${R}.log 2>&1
+python tools/summarize_ncu.py /tmp/prof_gemm_${R}.ncu-rep gpurun_out/${R}_gemm_full.csv
 echo "=== full: hadamard (tc3 K=172, tc2 K=28, mma.sync pow2) + quant + minmax + rmsn + gptq hessian"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"hadk_tc|act_quant_i8_kernel|minmax_tensor_kernel|fwht_|rmsn_quant|hessian_kernel" -c 24 -f -o gpurun_out/prof_mem_${R} python tools/profile_target.py all 16384 > gpurun_out/ncu_mem_${R}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"hadk_tc|act_quant_i8_kernel|minmax_tensor_kernel|fwht_|rmsn_quant|hessian_kernel" -c 30 -f -o /tmp/prof_mem_${R} python tools/profile_target.py all 16384 > gpurun_out/ncu_mem_${R}.log 2>&1
 tail -2 gpurun_out/ncu_mem_${R}.log
+python tools/summarize_ncu.py /tmp/prof_mem_${R}.ncu-rep gpurun_out/${R}_membound_full.csv
+# (the .ncu-rep files stay on the box: gpurun_out/ is limited to 64 MiB; the per-kernel details pages are text)
+ncu -i /tmp/prof_mem_${R}.ncu-rep --page details -k regex:"hadk_tc3|fwht_mma|rmsn_quant|hessian" 2>/dev/null | grep -v "^    -\+$" > gpurun_out/${R}_membound_details.txt
+ncu -i /tmp/prof_gemm_${R}.ncu-rep --page details 2>/dev/null | grep -v "^    -\+$" > gpurun_out/${R}_gemm_details.txt
 echo "=== microbench (all)"
 timeout 900 python tools/microbench.py --json gpurun_out/microbench_${R}.json > gpurun_out/microbench_${R}.log 2>&1
 tail -3 gpurun_out/microbench_${R}.log | cut -c1-200

@@ -168,6 +168,59 @@ def main():
                 rec(f"w4a8_gemm[{kname}]", f"M{M} K{K} N{N}", sec, best,
                     bytes_=N * K // 2 + M * K + 2 * M * N + 4 * N, ops_=2 * M * N * K)
                 del q, codes, w4, out
+    if want("gated"):
+        # Qwen-VL's MLP input side, w1 | w2 as one GEMM.  fused = a1 * silu(a2) in the
+        # epilogue ([M, F] written); unfused = the sibling-fused GEMM ([M, 2F] written) + torch's silu and mul
+        K, F = 4096, 11008
+        for M in ([4096] if a.quick else [4096, 16384]):
+            q = torch.randint(-128, 127, (M, K), dtype=torch.int8, device="cuda")
+            c1 = torch.randint(-8, 7, (F, K), dtype=torch.int8, device="cuda")
+            c2 = torch.randint(-8, 7, (F, K), dtype=torch.int8, device="cuda")
+            s_a = torch.rand(M, device="cuda") * 0.05
+            s_w = torch.rand(2 * F, device="cuda") * 0.01
+            w4g = ops.pack_w4(ops.interleave_gated(c1, c2))
+            w4c = ops.pack_w4(torch.cat([c1, c2]))
+            del c1, c2
+            out = torch.empty(M, F, dtype=torch.float16, device="cuda")
+            full = torch.empty(M, 2 * F, dtype=torch.float16, device="cuda")
+            sec, best = timeit(lambda: ops.w4a8_gemm_gated(q, w4g, s_a, s_w, F, out=out))
+            rec("w4a8_gemm_gated[fused]", f"M{M} K{K} F{F}", sec, best, bytes_=F * K + M * K + 2 * M * F, ops_=4 * M * F * K)
+            sec, best = timeit(lambda: ops.w4a8_gemm(q, w4c, s_a, s_w, 2 * F, out=full))
+            rec("w4a8_gemm[w1|w2]", f"M{M} K{K} N{2 * F}", sec, best, bytes_=F * K + M * K + 4 * M * F, ops_=4 * M * F * K)
+
+            def unfused():
+                ops.w4a8_gemm(q, w4c, s_a, s_w, 2 * F, out=full)
+                return full[:, :F] * torch.nn.functional.silu(full[:, F:])
+
+            sec, best = timeit(unfused)
+            rec("w4a8_gemm[w1|w2]+torch silu*mul", f"M{M} K{K} F{F}", sec, best, ops_=4 * M * F * K)
+            del q, w4g, w4c, out, full
+    if want("gptq"):
+        # one add_batch of a 2048-token sample (fp16 X^T X into the fp32 Hessian) against the
+        # reference's expression on the same device, and one 128-column block of fasterquant
+        import math
+        for C in (4096, 11008):
+            T = 2048
+            x = (torch.randn(T, C, device="cuda") * 2).half()
+            H = torch.zeros(C, C, device="cuda")
+            sec, best = timeit(lambda: ops.gptq_hessian_update(x, H, 3, 1))
+            rec("gptq_hessian_update", f"T{T} C{C}", sec, best, bytes_=8 * C * C + 2 * T * C, ops_=2 * T * C * C)
+
+            def ref_add_batch():  # gptq_utils.py:182-195
+                H.mul_(3 / 4)
+                inp = math.sqrt(2 / 4) * x.t().float()
+                H.add_(inp.matmul(inp.t()))
+
+            sec, best = timeit(ref_add_batch)
+            rec("gptq_add_batch[torch fp32]", f"T{T} C{C}", sec, best, ops_=2 * T * C * C)
+            del x, H
+        nrows, cols = 4096, 4096
+        W = torch.randn(nrows, cols, device="cuda") * 0.05
+        A = torch.randn(cols, cols, device="cuda")
+        Hinv = torch.linalg.cholesky(A @ A.t() / cols + 0.05 * torch.eye(cols, device="cuda"), upper=True).contiguous()
+        scale = W.abs().amax(dim=1) / 7
+        sec, best = timeit(lambda: ops.gptq_block(W, 0, 128, Hinv, scale, 7))
+        rec("gptq_block_f32", f"rows{nrows} x 128 columns", sec, best)
     if want("decode"):
         for K, N in [(4096, 4096), (4096, 11008), (11008, 4096)]:
             codes = torch.randint(-8, 7, (N, K), dtype=torch.int8, device="cuda")
