@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("MQUANT_B200_LIB") or os.path.join(_HERE, "libmquant_b
 
 MQ_FLAG_SPLIT = 1
 MQ_FLAG_FP32_HAD = 2
+MQ_FLAG_FAST_HAD = 4
 
 _lib = None
 

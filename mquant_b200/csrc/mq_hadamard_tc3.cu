@@ -57,6 +57,7 @@ constexpr int MAX_XS = 8, MAX_TG = 4;
 
 struct Cfg {
   int had_k, Kpad, kb2;  // Kpad = round_up(had_k, 16); kb2 = ceil(Kpad / 64) k-blocks of hadK
+  int src_k, expand;     // had_k = src_k * expand: the A operand is hadK (x) H_expand (n / src_k in {256, 512})
   int xrows;             // rows per X slot = per D1 tile
   int tpt;               // tiles per token
   int mt;                // M-tiles of MMA2
@@ -345,7 +346,17 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
                ((uint32_t)(((k & 63) >> 3) ^ (row & 7)) << 4) + (uint32_t)(k & 7) * 2u;
       };
       const int kcols = c.kb2 * 64;
-      if ((c.had_k & 3) == 0 && (reinterpret_cast<uintptr_t>(a.hadk) & 15u) == 0) {
+      if (c.expand > 1) {
+        // composite factor hadK (x) H_E: element (row, k) = hadK[row / E][k / E] * (-1)^popc((row % E) & (k % E))
+        // (the source matrix is a few hundred elements: L1 hits)
+        const int le = c.expand == 2 ? 1 : c.expand == 4 ? 2 : 3, em = c.expand - 1;
+        for (int e = tid; e < c.had_k * c.had_k; e += 256) {
+          const int row = e / c.had_k, k = e - row * c.had_k;
+          unsigned short v = __half_as_ushort(__ldg(a.hadk + (row >> le) * c.src_k + (k >> le)));
+          if (__popc((row & em) & (k & em)) & 1) v ^= (unsigned short)0x8000u;
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(sdst(row, k)), "h"(v) : "memory");
+        }
+      } else if ((c.had_k & 3) == 0 && (reinterpret_cast<uintptr_t>(a.hadk) & 15u) == 0) {
         const int nhalf = c.had_k * c.had_k / 4, nword = (nhalf + 1) / 2;
         const uint4* src = reinterpret_cast<const uint4*>(a.hadk);
         for (int w0 = tid; w0 < nword; w0 += 8 * 256) {
@@ -563,14 +574,16 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 template <int NS>
-static int launch(const HadArgs& a, cudaStream_t st) {
+static int launch(const HadArgs& a, cudaStream_t st, int expand = 1) {
   constexpr int P = 64 * NS;
   constexpr int G = 2 / NS;
   Params prm;
   prm.a = a;
   Cfg& c = prm.c;
-  c.had_k = a.had_k;
-  c.Kpad = round_up(a.had_k, 16);
+  c.src_k = a.had_k;
+  c.expand = expand;
+  c.had_k = a.had_k * expand;
+  c.Kpad = round_up(c.had_k, 16);
   c.kb2 = (c.Kpad + 63) / 64;
   c.mt = c.Kpad > 128 ? 2 : 1;
   c.t_bytes = NS * c.Kpad * 128;
@@ -637,10 +650,25 @@ extern "C" int mq_debug_hadk_tc3_stamps(long long* dst_host) {
 }
 #endif
 
-// had_k > 1, n / had_k in {64, 128}, fp16 rounding points of matmul_hadU_cuda: codes and/or fp16 output
-bool hadk_tc3_supported(const HadArgs& a) {
+// had_k > 1, fp16 rounding points of matmul_hadU_cuda, codes and/or fp16 output.  n / had_k in {64, 128}
+// directly; n / had_k in {256, 512} (InternVL2-8B: 14336 = 28 x 512) as the composite factor
+// hadK (x) H_E with E = n / had_k / 128 against 128-point blocks: the element index k * P + jh * 128 + jl
+// is (k * E + jh) * 128 + jl, and H_P = H_E (x) H_128.  The first fp16 rounding point then sits after
+// the 128-point part of the FHT instead of after all of it: same two roundings, different place, so the
+// result differs from the reference's by the size of its own intermediate-rounding noise (measured: up
+// to a few fp16 ulp on entries far below the row maximum).  That is more than the summation-order
+// tolerance of the default path, hence OPT-IN (MQ_FLAG_FAST_HAD); without the flag these shapes run on
+// mq_hadamard_tc2.cu, which keeps the reference's rounding points.
+static int tc3_expand(const mq::HadArgs& a) {
   const int P = a.n / a.had_k;
-  if (a.had_k <= 1 || a.had_k > 256 || (P != 64 && P != 128)) return false;
+  if (P == 64 || P == 128) return 1;
+  if ((P == 256 || P == 512) && a.had_k * (P / 128) <= 256 && (a.flags & MQ_FLAG_FAST_HAD)) return P / 128;
+  return 0;
+}
+
+bool hadk_tc3_supported(const HadArgs& a) {
+  if (a.had_k <= 1 || a.had_k > 256 || a.n % a.had_k != 0 || tc3_expand(a) == 0) return false;
+  const int P = a.n / a.had_k / tc3_expand(a);
   if (a.q == nullptr && a.y == nullptr) return false;
   if (a.flags & MQ_FLAG_FP32_HAD) return false;
   if (a.n_in % P != 0 || a.M >= (1ll << 31)) return false;
@@ -649,6 +677,8 @@ bool hadk_tc3_supported(const HadArgs& a) {
 }
 
 int launch_hadk_tc3(const HadArgs& a, cudaStream_t st) {
+  const int e = tc3_expand(a);
+  if (e > 1) return hadtc3::launch<2>(a, st, e);
   return a.n / a.had_k == 64 ? hadtc3::launch<1>(a, st) : hadtc3::launch<2>(a, st);
 }
 

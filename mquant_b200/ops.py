@@ -8,7 +8,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import MQ_FLAG_FP32_HAD, MQ_FLAG_SPLIT, check, lib
+from ._lib import MQ_FLAG_FAST_HAD, MQ_FLAG_FP32_HAD, MQ_FLAG_SPLIT, check, lib
 
 
 import functools
@@ -191,8 +191,9 @@ def act_quant_i8_dynamic(x, clip_ratio=1.0, n_out=None):
 
 @_on_device
 def hadamard(x, had_k=1, hadk=None, n=None, scales=None, modality=None, want_codes=False,
-             want_f16=True, split=False, fp32_had=False, want_row_scales=True):
-    """mq_hadamard_quant_i8.  Returns dict(y=fp16 [M,n] | None, q=int8 [M,n] | None, s_row, x0)."""
+             want_f16=True, split=False, fp32_had=False, want_row_scales=True, fast_had=False):
+    """mq_hadamard_quant_i8.  Returns dict(y=fp16 [M,n] | None, q=int8 [M,n] | None, s_row, x0).
+    fast_had: MQ_FLAG_FAST_HAD (n / had_k in {256, 512}: moved rounding point, see include/mquant_b200.h)."""
     _need_cuda(x, hadk, scales, modality)
     assert x.dtype == torch.float16
     x2 = _as_rows(x)
@@ -203,7 +204,7 @@ def hadamard(x, had_k=1, hadk=None, n=None, scales=None, modality=None, want_cod
     q = torch.empty((M, n), dtype=torch.int8, device=dev) if want_codes else None
     srow = torch.empty((M,), dtype=torch.float32, device=dev) if (want_codes and want_row_scales) else None
     x0 = torch.empty((M,), dtype=torch.float16, device=dev) if split else None
-    flags = (MQ_FLAG_SPLIT if split else 0) | (MQ_FLAG_FP32_HAD if fp32_had else 0)
+    flags = (MQ_FLAG_SPLIT if split else 0) | (MQ_FLAG_FP32_HAD if fp32_had else 0) | (MQ_FLAG_FAST_HAD if fast_had else 0)
     if hadk is not None:
         assert hadk.dtype == torch.float16 and hadk.is_contiguous() and hadk.shape == (had_k, had_k)
     check(lib().mq_hadamard_quant_i8(_ptr(x2), _ld(x2), _ptr(q), _ptr(y), _ptr(srow), _ptr(x0),

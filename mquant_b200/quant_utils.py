@@ -297,6 +297,7 @@ class ActQuantWrapper(torch.nn.Module):
         self.online_partial_had = False
         self.had_dim = 0
         self.fp32_had = False
+        self.fast_had = False  # opt-in MQ_FLAG_FAST_HAD (n / K in {256, 512}: moved fp16 rounding point, 3x faster)
         self.split = False
         # new
         self.pad_to = None       # fold utils.revise_down_input into the fused kernel
@@ -410,7 +411,7 @@ class ActQuantWrapper(torch.nn.Module):
             hk = hadamard_utils.hadK_device(self.K, x.device) if self.K > 1 else None
             r = ops.hadamard(x2, had_k=self.K, hadk=hk, n=n, scales=scales, modality=modality,
                              want_codes=True, want_f16=False, split=self.split, fp32_had=self.fp32_had,
-                             want_row_scales=modality is not None)
+                             want_row_scales=modality is not None, fast_had=self.fast_had)
             q, srow, x0 = r["q"], r["s_row"], r["x0"]
             if q.shape[1] != pk["Kp"]:
                 q = torch.nn.functional.pad(q, (0, pk["Kp"] - q.shape[1]))
@@ -433,7 +434,7 @@ class ActQuantWrapper(torch.nn.Module):
             if x.dtype not in (torch.float16, torch.bfloat16):
                 raise NotImplementedError("online Hadamard: fp16 / bf16 activations only")
             xh = x if x.dtype == torch.float16 else x.clamp(-65504.0, 65504.0).to(torch.float16)
-            y = ops.hadamard(xh, had_k=self.K, hadk=hk, n=n, fp32_had=self.fp32_had)["y"]
+            y = ops.hadamard(xh, had_k=self.K, hadk=hk, n=n, fp32_had=self.fp32_had, fast_had=self.fast_had)["y"]
             return y.reshape(*x.shape[:-1], n).to(x.dtype)
         if self.online_partial_had:
             return self._partial_had(x)

@@ -34,6 +34,9 @@ def force(ops):
         def hadamard_cuda_cores(self, on):
             lib().mq_debug_force_hadamard_kernel(1 if on else 0)
 
+        def hadamard_tc2(self):  # FWHT in registers + hadK on tcgen05 (second generation)
+            lib().mq_debug_force_hadamard_kernel(2)
+
     yield F()
     lib().mq_debug_force_gemm_kernel(0)
     lib().mq_debug_force_hadamard_kernel(0)
@@ -325,13 +328,17 @@ def test_hadamard_pow2(ops, n):
     had_check(ops, x, n, 1, s, fp32_had=True)
 
 
-@pytest.mark.parametrize("path", ["default", "simt"])
+@pytest.mark.parametrize("path", ["default", "tc2", "simt"])
 @pytest.mark.parametrize("n,n_in", [(11008, 11008), (13824, 13696), (14336, 14336), (19968, 18944),
                                     (5120, 5120), (3584, 3584), (3072, 3072), (5120 * 2, 5120 * 2)])
 def test_hadamard_nonpow2(ops, force, path, n, n_in):
-    """default = FWHT in registers + hadK on tcgen05 (mq_hadamard_tc2.cu; P = 64 .. 512),
-    simt = the CUDA-core kernel."""
-    force.hadamard_cuda_cores(path == "simt")
+    """default = both Kronecker factors on tcgen05 (mq_hadamard_tc3.cu) for n / had_k = 64 / 128 and
+    FWHT in registers + hadK on tcgen05 (mq_hadamard_tc2.cu) for 256 / 512; tc2 = the latter forced
+    for every shape; simt = the CUDA-core kernel."""
+    if path == "tc2":
+        force.hadamard_tc2()
+    else:
+        force.hadamard_cuda_cores(path == "simt")
     k = O.get_hadK(n)[1]
     assert k > 1
     rng = np.random.default_rng(n)
@@ -343,6 +350,37 @@ def test_hadamard_nonpow2(ops, force, path, n, n_in):
         had_check(ops, x, n, k, s, split=True)
         mod = (rng.random(9) < 0.5).astype(np.uint8)
         had_check(ops, x, n, k, s, modality=mod, s_vis=np.float32(np.float16(s * 2.5)))
+
+
+@pytest.mark.parametrize("n,n_in,M", [(14336, 14336, 9), (14336, 14336, 1000), (3072, 3072, 70), (10240, 10240, 33)])
+def test_hadamard_fast_had_flag(ops, n, n_in, M):
+    """MQ_FLAG_FAST_HAD (opt-in; n / had_k in {256, 512}: InternVL2-8B's 14336 = 28 x 512): the FHT factor
+    is split as H_E (x) H_128, the H_E part joins hadK on the tensor core, and the first fp16 rounding
+    point moves from after the whole FHT to after its 128-point part.  Stated tolerance against the
+    oracle (= the reference's rounding points): every output within 4 fp16 ulp OF ITS ROW'S MAXIMUM
+    (the two results differ by the intermediate-rounding noise, which scales with the row, not the
+    entry), relative Frobenius error <= 2^-10, INT8 codes within +-1, differing on < 1 % of the entries.
+    Without the flag the same call runs the kernel that keeps the reference's rounding points."""
+    from mquant_b200 import hadamard_utils as hu
+
+    k = O.get_hadK(n)[1]
+    rng = np.random.default_rng(n + M)
+    x = rnd_act(rng, M, n_in)
+    s = np.float32(np.float16(np.abs(x.astype(np.float32)).max() / 127 / 4))
+    hk = hu.hadK_device(k, "cuda")
+    scales = ops.make_scales(float(s), float(s), "cuda")
+    r = ops.hadamard(dev(x), had_k=k, hadk=hk, n=n, scales=scales, want_codes=True, want_f16=True, fast_had=True)
+    exact = ops.hadamard(dev(x), had_k=k, hadk=hk, n=n, scales=scales, want_codes=True, want_f16=True)
+    y, q = host(r["y"]).astype(np.float32), host(r["q"]).astype(np.int32)
+    rows = slice(0, min(M, 64))
+    ref = O.matmul_hadU_cuda(O.pad_last(x[rows], n)).astype(np.float32)
+    ulp_rowmax = np.spacing(np.abs(ref).max(axis=1, keepdims=True).astype(np.float16)).astype(np.float32)
+    assert np.all(np.abs(y[rows] - ref) <= 4 * ulp_rowmax)
+    assert np.linalg.norm(y[rows] - ref) <= 2.0 ** -10 * np.linalg.norm(ref)
+    # the quantiser stage is exact on the kernel's own rotated values
+    assert np.array_equal(q, O.act_quant_codes(host(r["y"]), s).astype(np.int32))
+    d = np.abs(q - host(exact["q"]).astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-2, (int(d.max()), float((d > 0).mean()))
 
 
 @pytest.mark.parametrize("n,n_in,M", [(11008, 11008, 9), (11008, 11008, 300), (13824, 13696, 5),

@@ -151,6 +151,10 @@ def main():
             sec, best = timeit(lambda: ops.hadamard(x, had_k=K_, hadk=hk, n=n, scales=scales, modality=mod,
                                                     want_codes=True, want_f16=False))
             rec(f"hadamard_quant_k{K_}", f"{M}x{n_in}->{n}", sec, best, bytes_=(2 * n_in + n) * M + M)
+            if K_ > 1 and n // K_ in (256, 512):
+                sec, best = timeit(lambda: ops.hadamard(x, had_k=K_, hadk=hk, n=n, scales=scales, modality=mod,
+                                                        want_codes=True, want_f16=False, fast_had=True))
+                rec(f"hadamard_quant_k{K_}[fast_had]", f"{M}x{n_in}->{n}", sec, best, bytes_=(2 * n_in + n) * M + M)
             del x
 
     if want("gemm"):
