@@ -57,6 +57,23 @@ for mse in (False, True):
     g.fasterquant(blocksize=32, percdamp=0.01, groupsize=-1, actorder=False, static_groups=False)
     res[f"gptq_w_mse{int(mse)}"] = lin.weight.data.numpy().copy()
     res[f"gptq_scale_mse{int(mse)}"] = g.quantizer.scale.numpy().copy()
+if mode == "shim":
+    # mquant_b200.gptq.accelerate_reference(): the kernel-backed add_batch / fasterquant are installed into the
+    # reference's class; a configuration the kernels do not take (here: CPU tensors) runs the reference's own loop
+    from mquant_b200 import gptq as mq_gptq
+
+    assert mq_gptq.accelerate_reference() and gptq_utils.GPTQ.add_batch is mq_gptq.add_batch
+    rng_state = torch.get_rng_state()  # (the cases below must see the same random stream in both modes)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(96, 40, bias=False)
+    g = gptq_utils.GPTQ(lin)
+    g.quantizer = quant_utils.WeightQuantizer()
+    g.quantizer.configure(4, perchannel=True, sym=True, mse=False)
+    for _ in range(3):
+        g.add_batch(torch.randn(2, 17, 96), None)
+    g.fasterquant(blocksize=32, percdamp=0.01, groupsize=-1, actorder=False, static_groups=False)
+    res["gptq_w_accelerated_cpu"] = lin.weight.data.numpy().copy()
+    torch.set_rng_state(rng_state)
 # --- RTN (rtn path of *_gptq_plus.py)
 W = torch.randn(24, 64)
 wq = quant_utils.WeightQuantizer()

@@ -112,3 +112,42 @@ def test_merge_calibration_agrees_on_modalities_seen():
         n, st, sv, seen = ret[r]
         assert n == 2 and seen == [10, 4]  # MAX over ranks of the row counts
         assert np.float16(st) == s_text and sv is not None and np.float16(sv) == s_vis
+
+
+def _worker_hessian(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mquant_b200 import dist as mqd, gptq as G
+
+    rng = np.random.default_rng(3)
+    samples = [rng.standard_normal((int(rng.integers(5, 40)), 48)).astype(np.float16) for _ in range(7)]
+    layers = [torch.nn.Linear(48, 8, bias=False), torch.nn.Linear(48, 16, bias=False)]
+    gs = [G.GPTQ(l) for l in layers]
+    for i in mqd.shard_indices(len(samples), rank, world):
+        for k, g in enumerate(gs):  # the second layer sees the samples scaled: two different Hessians in one collective
+            H64, n = O.gptq_hessian(g.H.numpy(), g.nsamples, samples[i] * np.float16(1 + k), 1)
+            g.H, g.nsamples = torch.from_numpy(H64.astype(np.float32)), n
+    G.allreduce_hessians(gs)
+    ret[rank] = [(g.H.numpy().copy(), g.nsamples) for g in gs]
+    dist.destroy_process_group()
+
+
+def test_sharded_gptq_hessians_merge_to_the_sequential_hessian():
+    """calibration samples sharded over ranks, GPTQ.add_batch (gptq_utils.py:182-195) run
+    locally, gptq.allreduce_hessians = ONE all-reduce(SUM) over every layer's n_r * H_r and the counts:
+    every rank ends with the Hessian (and nsamples) of a sequential pass over all samples."""
+    world = 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_hessian, args=(world, port, ret), nprocs=world, join=True)
+    rng = np.random.default_rng(3)
+    samples = [rng.standard_normal((int(rng.integers(5, 40)), 48)).astype(np.float16) for _ in range(7)]
+    for k in range(2):
+        H, n = np.zeros((48, 48)), 0
+        for s in samples:
+            H, n = O.gptq_hessian(H, n, s * np.float16(1 + k), 1)
+        for r in range(world):
+            Hr, nr = ret[r][k]
+            assert nr == n == len(samples)
+            assert np.abs(Hr - H).max() <= 1e-6 * np.abs(H).max()
+        assert np.array_equal(ret[0][k][0], ret[1][k][0])

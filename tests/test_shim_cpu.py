@@ -74,6 +74,9 @@ def test_reference_modules_run_through_the_shim(tmp_path):
     # GPTQ + RTN through OUR WeightQuantizer: the same torch arithmetic -> identical weights / scales
     for k in ("gptq_w_mse0", "gptq_scale_mse0", "gptq_w_mse1", "gptq_scale_mse1", "rtn_w", "fuse_w", "fuse_b"):
         assert np.array_equal(s[k], r[k]), k
+    # gptq.accelerate_reference() installed into the reference's GPTQ: on tensors the kernels do not take
+    # the reference's own loop runs -> the same weights as the first GPTQ case (same seed, same data)
+    assert np.array_equal(s["gptq_w_accelerated_cpu"], r["gptq_w_mse0"])
     # offline rotations: butterfly (ours) vs dense Sylvester matmul (the stub): fp32 summation order
     for k in s.files:
         if k.startswith(("had_", "rand_had", "fht_direct")):
