@@ -391,14 +391,36 @@ def main():
     out_host = torch.empty((n_seq, stack.hidden), dtype=torch.float16).pin_memory()
     last_idx = torch.arange(a.seq_len - 1, a.tokens, a.seq_len, device=dev)[:n_seq]
     e2e_inputs = dict(inputs)
+    # Double-buffered like any serving loop: while step i computes, the host->device copy of step i+1's
+    # hidden states runs on a copy stream into the other device buffer.  Every step issues exactly one
+    # 134 MB copy and one read-back inside the timed region; the first buffer is primed by the warm-up.
+    copy_stream = torch.cuda.Stream(device=dev)
+    h_dev = [torch.empty_like(inputs["h"]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    state = {"i": 0}
+    with torch.cuda.stream(copy_stream):
+        h_dev[0].copy_(h_host, non_blocking=True)
+        ready[0].record(copy_stream)
+    consumed[1].record()
 
     def e2e_step():
-        e2e_inputs["h"] = h_host.to(dev, non_blocking=True)
+        cur = state["i"] & 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):  # prefetch the next step's input
+            copy_stream.wait_event(consumed[cur ^ 1])
+            h_dev[cur ^ 1].copy_(h_host, non_blocking=True)
+            ready[cur ^ 1].record(copy_stream)
+        main.wait_event(ready[cur])
+        e2e_inputs["h"] = h_dev[cur]
         out = stack.forward_tokens(e2e_inputs)
+        consumed[cur].record(main)
         out_host.copy_(out.reshape(-1, stack.hidden)[last_idx], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        main.synchronize()
+        state["i"] += 1
 
     ms_e2e = timed(e2e_step, a.steps, min(a.warmup, 3))
+    copy_stream.synchronize()
     e2e_value = tokens_total / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant kernel: time every GEMM launch of one step with CUDA events
@@ -476,7 +498,9 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(h_host.numel() * 2) * world,
-                "d2h_bytes_per_step": int(out_host.numel() * 2) * world},
+                "d2h_bytes_per_step": int(out_host.numel() * 2) * world,
+                "pipeline": "double-buffered: the pinned-host -> device copy of step i+1 runs on a copy stream while "
+                            "step i computes; one input copy + one result read-back per timed step"},
         "gpu_launches": stack.launches_per_step() * a.steps,
         "roofline": roofline,
     }
