@@ -250,12 +250,13 @@ int mq_gptq_block_f32(float* W, int64_t ldw, const float* Hinv1, int64_t ldh, co
                       void* stream);
 
 /* Which kernel mq_w4a8_gemm_ws runs for a shape and workspace size: 1 = weight-streaming dp4a
- * (decode), 2 = split-K tcgen05, 3 = 128 x 256 tcgen05, 4 = 256 x 256 tcgen05; 0 = invalid
- * shape.  Pure function of its arguments and the SM count (diagnostics / tests). */
+ * (decode), 2 = split-K tcgen05, 4 = 256 x 256 tcgen05, 5 = 128 channels x 256 tokens with the
+ * converted weights resident in tensor memory (3 = the older 128 x 256 kernel, never planned);
+ * 0 = invalid shape.  Pure function of its arguments and the SM count (diagnostics / tests). */
 int mq_w4a8_gemm_plan(int64_t M, int64_t N, int64_t K, size_t workspace_bytes);
 
 /* Test / tooling overrides of the dispatchers (process-wide; return the previous value):
- *   mq_debug_force_gemm_kernel(3 | 4)  always run the 128 x 256 / 256 x 256 tcgen05 kernel, 0 = auto
+ *   mq_debug_force_gemm_kernel(3 | 4 | 5)  always run the 128 x 256 / 256 x 256 / weights-in-TMEM tcgen05 kernel, 0 = auto
  *   mq_debug_force_hadamard_kernel(1)  CUDA-core Hadamard kernels only (cross-checks), 2 = the
  *                                      previous tensor-core generation for had_k > 1, 0 = auto */
 int mq_debug_force_gemm_kernel(int kernel);

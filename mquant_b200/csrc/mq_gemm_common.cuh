@@ -84,6 +84,8 @@ int launch_w4a8_gemm_v2(const CUtensorMap& tmap_a, const Params& p, cudaStream_t
 // gated: interleaved w1 | w2 rows, output [M, N / 2] = a1 * silu(a2) (tmap_out describes that tensor)
 int launch_w4a8_gemm_v4(const CUtensorMap& tmap_a, const CUtensorMap& tmap_out, const Params& p, cudaStream_t st,
                         bool gated = false);
+// mq_gemm_w4a8_v5.cu: 128 channels x 256 tokens per CTA, converted weights as the TMEM-resident A operand
+int launch_w4a8_gemm_v5(const CUtensorMap& tmap_a, const Params& p, cudaStream_t st);
 // mq_gemm_w4a8_sk.cu: split-K flavour of the 128 x 256 kernel for mid-sized M (int32 partial sums in
 // a caller-provided self-cleaning workspace); splitk_factor() == 1 means "not worth it"
 int splitk_factor(int64_t M, int64_t N, int64_t K);

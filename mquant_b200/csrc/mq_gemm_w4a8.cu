@@ -7,7 +7,9 @@
 // operation (oracle/mq_oracle.py:qlinear_int) and reproduced bit for bit by every kernel:
 //
 //   mq_gemm_w4a8_v4.cu   256 x 256 tile, one weight conversion shared by two M halves (large M)
-//   mq_gemm_w4a8_v2.cu   128 x 256 tile, double-buffered TMEM accumulator (one wave of tiles)
+//   mq_gemm_w4a8_v5.cu   128 channels x 256 tokens, converted weights as the TMEM-resident A operand
+//                        (mid-sized M: one or two waves of tiles)
+//   mq_gemm_w4a8_v2.cu   128 x 256 tile, weights converted into shared memory (forced / split-K base)
 //   mq_gemm_w4a8_sk.cu   split-K flavour of the 128 x 256 kernel (mid-sized M)
 //   mq_gemv_w4a8.cu      weight-streaming dp4a kernel (decode)
 //
@@ -33,22 +35,29 @@ constexpr int BK = 128;  // int8 elements per k-block
 static std::atomic<int> g_force_kernel{0};
 
 // Which kernel the dispatcher runs for a shape (no environment overrides):
-//   1 weight-streaming dp4a kernel (decode)   2 split-K tcgen05 kernel (mid-sized M)
-//   3 128 x 256 tcgen05 kernel                4 256 x 256 tcgen05 kernel (large M)
+//   1 weight-streaming dp4a kernel (decode)      2 split-K tcgen05 kernel (few tiles, long K)
+//   4 256 x 256 tcgen05 kernel (large M)         5 128-channel x 256-token kernel, weights in TMEM
+//   (3 = the 128 x 256 kernel: superseded by 5 for every shape measured, reachable by forcing only)
 static int plan_kernel(int64_t M, int64_t N, int64_t K, size_t workspace_bytes) {
   const int64_t n_tiles = (N + BN - 1) / BN, k_tiles = K / BK;
   const bool gemv_shape = M <= 8 || (M <= 16 && n_tiles < 32);
   if (gemv_shape && workspace_bytes > 0 && workspace_bytes >= gemv_workspace_bytes(N)) return 1;
-  if (workspace_bytes > 0 && splitk_factor(M, N, K) >= 2 && workspace_bytes >= splitk_workspace_bytes(M, N, K)) return 2;
-  // the cheaper of the 256 x 256 kernel and the 128 x 256 kernel under a wave model fitted to
-  // tools/latency.py (us per wave of one tile per SM: 0.506 K + 6.5 vs 0.60 K + 7.5, K in k-blocks;
-  // profiles/README.md): the 128 x 256 kernel only wins while it needs a single wave
+  // Wave model fitted to tools/latency.py (hot code, cold weights; us per wave of one tile per SM, K in
+  // k-blocks; profiles/r2_gemm_latency.log): 256 x 256 tiles 0.60 K + 7.5, 128 x 256 (weights in TMEM)
+  // 0.35 K + 6.5, a split-K item 0.55 K/split + 6.5 + 8 for the reduction.
   const int64_t sms = num_sms();
-  const int64_t waves2 = (((M + 127) / 128) * n_tiles + sms - 1) / sms;
   const int64_t waves4 = (((M + 255) / 256) * n_tiles + sms - 1) / sms;
-  const double cost2 = (double)waves2 * (0.506 * k_tiles + 6.5);
+  const int64_t waves5 = (((M + 255) / 256) * ((N + 127) / 128) + sms - 1) / sms;
   const double cost4 = (double)waves4 * (0.60 * k_tiles + 7.5);
-  return cost4 < cost2 ? 4 : 3;
+  const double cost5 = (double)waves5 * (0.35 * k_tiles + 6.5);
+  int best = cost4 < cost5 ? 4 : 5;
+  const double cost = cost4 < cost5 ? cost4 : cost5;
+  const int split = splitk_factor(M, N, K);
+  if (workspace_bytes > 0 && split >= 2 && workspace_bytes >= splitk_workspace_bytes(M, N, K)) {
+    const double cost_sk = 0.55 * (double)((k_tiles + split - 1) / split) + 14.5;
+    if (cost_sk < cost) best = 2;
+  }
+  return best;
 }
 }  // namespace gemm
 }  // namespace mq
@@ -120,7 +129,9 @@ static int gemm_impl(const int8_t* qa, int64_t lda, const uint8_t* w4, const flo
   // kernel choice: plan_kernel(), unless a test / tool forces one of the two persistent kernels
   int kernel = plan_kernel(M, N, K, workspace != nullptr ? workspace_bytes : 0);
   const int forced = g_force_kernel.load(std::memory_order_relaxed);
-  if (forced == 3 || forced == 4) kernel = forced;
+  if (forced >= 3 && forced <= 5) kernel = forced;
+  if (forced == 2 && workspace != nullptr && splitk_factor(M, N, K) >= 2 && workspace_bytes >= splitk_workspace_bytes(M, N, K))
+    kernel = 2;  // (tests: the split-K kernel wherever it is applicable)
   if (p.dbg != 0 && kernel < 3) kernel = 3;  // the probes live in the persistent kernels
   if (gated) kernel = 4;                     // (the caller has checked that this is the planned kernel)
   cudaStream_t st = (cudaStream_t)stream;
@@ -152,6 +163,12 @@ static int gemm_impl(const int8_t* qa, int64_t lda, const uint8_t* w4, const flo
     const int rc = launch_w4a8_gemm_v4(tmap, tmap_out, p, st, gated);
     if (rc != MQ_OK) return rc;
     MQ_LAUNCH_CHECK("w4a8_gemm_v4_kernel");
+    return MQ_OK;
+  }
+  if (kernel == 5) {
+    const int rc = launch_w4a8_gemm_v5(tmap, p, st);
+    if (rc != MQ_OK) return rc;
+    MQ_LAUNCH_CHECK("w4a8_gemm_v5_kernel");
     return MQ_OK;
   }
   const int rc = launch_w4a8_gemm_v2(tmap, p, st);
@@ -217,7 +234,7 @@ extern "C" int mq_w4a8_gemm_gated_ws(const int8_t* qa, int64_t lda, const uint8_
   MQ_REQUIRE(K > 0 && K % BK == 0, "mq_w4a8_gemm_gated: K=%lld must be a multiple of %d", (long long)K, BK);
   int kernel = plan_kernel(M, N2, K, workspace != nullptr ? workspace_bytes : 0);
   const int forced = g_force_kernel.load(std::memory_order_relaxed);
-  if (forced == 3 || forced == 4) kernel = forced;
+  if (forced >= 3 && forced <= 5) kernel = forced;
   if (kernel == 4)
     return gemm_impl(qa, lda, w4, s_a, s_a_per_row, s_w, bias, nullptr, nullptr, out, ldo, M, N2, K, workspace,
                      workspace_bytes, stream, true);
@@ -230,5 +247,5 @@ extern "C" int mq_w4a8_gemm_gated_ws(const int8_t* qa, int64_t lda, const uint8_
 }
 
 extern "C" int mq_debug_force_gemm_kernel(int kernel) {
-  return mq::gemm::g_force_kernel.exchange(kernel == 3 || kernel == 4 ? kernel : 0);
+  return mq::gemm::g_force_kernel.exchange(kernel >= 2 && kernel <= 5 ? kernel : 0);
 }

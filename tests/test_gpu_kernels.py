@@ -29,7 +29,7 @@ def force(ops):
 
     class F:
         def gemm(self, kernel):
-            lib().mq_debug_force_gemm_kernel({"default": 0, "v2": 3, "v4": 4}[kernel])
+            lib().mq_debug_force_gemm_kernel({"default": 0, "sk": 2, "v2": 3, "v4": 4, "v5": 5}[kernel])
 
         def hadamard_cuda_cores(self, on):
             lib().mq_debug_force_hadamard_kernel(1 if on else 0)
@@ -582,7 +582,7 @@ def test_gemm_simt_matches_oracle(ops, M, N, K, per_row, bias, split):
     assert np.array_equal(bits16(O.qlinear_int(qa, s_a, cw, s_w, b, x0, w0)), bits16(oracle_gemm(case)))
 
 
-@pytest.mark.parametrize("kernel", ["default", "v2", "v4"])
+@pytest.mark.parametrize("kernel", ["default", "v2", "v4", "v5"])
 @pytest.mark.parametrize("M,N,K,per_row,bias,split", [
     (128, 256, 128, False, False, False),     # one tile, one k-block
     (128, 256, 512, False, False, False),     # pipeline wraps once
@@ -625,17 +625,31 @@ def test_gemm_decode_weight_streaming_path(ops, M, N, K, per_row, bias, split):
     (500, 768, 2048, True, False, True),
     (17, 4096, 11008, True, True, False),
 ])
-def test_gemm_split_k_path(ops, M, N, K, per_row, bias, split):
-    """Mid-sized M takes the split-K kernel (int32 partial sums in the self-cleaning workspace,
-    the last CTA of a tile applies the epilogue): bit-exact, also back to back on one workspace."""
+def test_gemm_split_k_path(ops, force, M, N, K, per_row, bias, split):
+    """The split-K kernel (int32 partial sums in the self-cleaning workspace, the last CTA of a tile
+    applies the epilogue) wherever it is applicable (the dispatcher takes it when its cost model beats
+    the one-wave kernels: few tiles, long K): bit-exact, also back to back on one workspace."""
     from mquant_b200._lib import lib
 
     assert lib().mq_w4a8_gemm_workspace_bytes(M, N, K) > 0
+    force.gemm("sk")
     rng = np.random.default_rng(M + N + K)
     for rep in range(3):
         case = gemm_case(rng, M, N, K, per_row, bias, split)
         got = run_gemm(ops, case, simt=False)
         assert np.array_equal(bits16(got), bits16(oracle_gemm(case))), rep
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 4096, 4096), (1024, 4096, 11008), (700, 4096 + 8, 4096)])
+def test_gemm_single_request_default_dispatch(ops, M, N, K):
+    """One 1024-token request (one wave of tiles): the DEFAULT dispatcher must pick the kernel that keeps
+    the converted weights in tensor memory (mq_gemm_w4a8_v5.cu: weights = the A operand, accumulator
+    transposed), bit-exact vs the exact-integer oracle incl. ragged M / N, bias and the split term."""
+    from mquant_b200._lib import lib
+
+    assert lib().mq_w4a8_gemm_plan(M, N, K, lib().mq_w4a8_gemm_workspace_bytes(M, N, K)) == 5
+    case = gemm_case(np.random.default_rng(M + N + K), M, N, K, True, True, K == 4096)
+    assert np.array_equal(bits16(run_gemm(ops, case, simt=False)), bits16(oracle_gemm(case)))
 
 
 # The shapes the headline benchmark runs (bench.py: Qwen-VL-Chat prefill, 16384 tokens per step; q|k|v

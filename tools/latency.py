@@ -34,7 +34,7 @@ def main():
                 if kern == "default":
                     lib().mq_debug_force_gemm_kernel(0)
                 else:
-                    lib().mq_debug_force_gemm_kernel({"v2": 3, "v4": 4}.get(kern, 0))
+                    lib().mq_debug_force_gemm_kernel({"v2": 3, "v4": 4, "v5": 5}.get(kern, 0))
                 for i in range(R):
                     ops.w4a8_gemm(q, w4s[i], s_a, s_w, N, out=out)
                 torch.cuda.synchronize()
