@@ -13,7 +13,9 @@ import sys, torch
 sys.path.insert(0, '.')
 from mquant_b200 import ops
 M = 16384
-for K, N in ((4096, 12288), (4096, 4096), (4096, 22016), (11008, 4096)):  # q|k|v, o, w1|w2 (sibling fused), down
+for K, N in ((4096, 12288), (4096, 4096), (4096, 22016), (11008, 4096), (-4096, 4096), (-11008, 4096)):  # q|k|v, o, w1|w2 (sibling fused), down; K < 0: one 1024-token request (v5 kernel)
+    M = 1024 if K < 0 else 16384
+    K = abs(K)
     q = torch.randint(-128, 127, (M, K), dtype=torch.int8, device="cuda")
     w4 = ops.pack_w4(torch.randint(-8, 7, (N, K), dtype=torch.int8, device="cuda"))
     s_a = torch.rand(M, device="cuda") * 0.1
@@ -29,10 +31,12 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"had
 tail -2 gpurun_out/ncu_mem_${R}.log
 python tools/summarize_ncu.py /tmp/prof_mem_${R}.ncu-rep gpurun_out/${R}_membound_full.csv
 # (the .ncu-rep files stay on the box: gpurun_out/ is limited to 64 MiB; the per-kernel details pages are text)
-ncu -i /tmp/prof_mem_${R}.ncu-rep --page details -k regex:"hadk_tc3|fwht_mma|rmsn_quant|hessian" 2>/dev/null | grep -v "^    -\+$" > gpurun_out/${R}_membound_details.txt
+ncu -i /tmp/prof_mem_${R}.ncu-rep --page details -k regex:"hadk_tc3|fwht_mma|rmsn_quant|hessian|w4a8_gemm_v5" 2>/dev/null | grep -v "^    -\+$" > gpurun_out/${R}_membound_details.txt
 ncu -i /tmp/prof_gemm_${R}.ncu-rep --page details 2>/dev/null | grep -v "^    -\+$" > gpurun_out/${R}_gemm_details.txt
 echo "=== microbench (all)"
 timeout 900 python tools/microbench.py --json gpurun_out/microbench_${R}.json > gpurun_out/microbench_${R}.log 2>&1
+timeout 600 python tools/microbench.py --only hadsweep,gated,gptq --json gpurun_out/microbench2_${R}.json > gpurun_out/microbench2_${R}.log 2>&1
+timeout 600 python tools/latency.py --shapes 4096x4096,4096x12288,4096x22016,11008x4096 --ms 256,1024 --kernels default,v2,v4,v5 > gpurun_out/latency_${R}.log 2>&1
 tail -3 gpurun_out/microbench_${R}.log | cut -c1-200
 echo "=== bench"
 timeout 900 python bench.py > gpurun_out/bench_${R}.json 2> gpurun_out/bench_${R}.err
