@@ -383,7 +383,18 @@ def main():
     # ---- TTFT of ONE request (seq_len tokens alone on the GPU): the latency end of the metric;
     # ttft_ms_per_request below is the amortised figure of the batched step
     one = {k: (v[:a.seq_len] if hasattr(v, "shape") else v) for k, v in inputs.items()}
-    ms_single = timed(lambda: stack.forward_tokens(one), 5, 3)
+    ms_single_eager = timed(lambda: stack.forward_tokens(one), 5, 3)
+    # the same request as ONE CUDA graph (256 launches replayed without host work between them)
+    ms_single, single_mode = ms_single_eager, "eager"
+    try:
+        graph, g_out = stack.capture_tokens(one)
+        eager_out = stack.forward_tokens(one)
+        graph.replay()
+        torch.cuda.synchronize()
+        if torch.equal(g_out, eager_out):
+            ms_single, single_mode = timed(graph.replay, 5, 3), "cuda_graph"
+    except Exception as e:  # noqa: BLE001  (capture is an optimisation of the latency figure only)
+        single_mode = f"eager (graph capture failed: {type(e).__name__})"
 
     # ---- e2e: host buffers -> device -> path -> host, every step
     h_host = torch.empty(inputs["h"].shape, dtype=torch.float16).pin_memory()
@@ -495,6 +506,8 @@ def main():
                    "l2": "inputs+weights per step (>3 GB) exceed the 126 MB L2; no flush needed"},
         "ttft_ms_per_request": ms_step / n_seq,
         "ttft_single_request_ms": ms_single,
+        "ttft_single_request_mode": single_mode,
+        "ttft_single_request_eager_ms": ms_single_eager,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(h_host.numel() * 2) * world,

@@ -195,6 +195,25 @@ class QuantLinearStack(torch.nn.Module):
         return out
 
     @torch.no_grad()
+    def capture_tokens(self, inputs, warmup=2):
+        """The same pass as ``forward_tokens(inputs)`` captured into a CUDA graph (one request's launches --
+        8 kernels per layer -- replayed without host work between them; at 1024 tokens the eager loop is
+        close to launch bound).  ``inputs`` are static buffers: refill them in place, ``graph.replay()``,
+        read ``out``.  Returns (graph, out)."""
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=cur.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):  # warm-up on the capture stream: workspaces / attributes exist before capture
+            for _ in range(warmup):
+                self.forward_tokens(inputs)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            out = self.forward_tokens(inputs)
+        return graph, out
+
+    @torch.no_grad()
     def observe_tokens(self, inputs):
         """Calibration pass of the hot path only: online rotation (fp16 output) + observer update of
         every wrapper, without the fp16 Linear the reference's calibration forward also runs (that

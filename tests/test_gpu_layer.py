@@ -410,6 +410,27 @@ def test_sibling_fusion_is_bit_identical(qu):
 
 
 @torch.no_grad()
+def test_cuda_graph_of_one_request_matches_eager(qu):
+    """QuantLinearStack.capture_tokens: one request's launches as ONE CUDA graph (static input buffers,
+    every kernel enqueued on the capturing stream, no host synchronisation on the path) -- replays give
+    the eager result bit for bit, also after the inputs were refilled in place."""
+    from mquant_b200.prefill import QuantLinearStack
+
+    stack = QuantLinearStack("qwenvl-9.6b", n_layers=2, device="cuda", calib_tokens=256)
+    inputs = stack.make_inputs(1024, "cuda", seed=3, seq_len=1024, visual_span=256)
+    graph, out = stack.capture_tokens(inputs)
+    for seed in (3, 4):
+        fresh = stack.make_inputs(1024, "cuda", seed=seed, seq_len=1024, visual_span=256)
+        for k, v in fresh.items():
+            if torch.is_tensor(v):
+                inputs[k].copy_(v)
+        want = stack.forward_tokens(inputs).clone()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out.view(torch.int16), want.view(torch.int16)), seed
+
+
+@torch.no_grad()
 def test_aifs_reordered_tokens_through_quantlinear(qu):
     """the quantized Linears are position-wise, so visual-tokens-first reordering
     (mquant_b200/aifs.py) with the two-segment modality mask gives bit-identically the reordered
