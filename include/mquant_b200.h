@@ -258,7 +258,9 @@ int mq_w4a8_gemm_plan(int64_t M, int64_t N, int64_t K, size_t workspace_bytes);
 /* Test / tooling overrides of the dispatchers (process-wide; return the previous value):
  *   mq_debug_force_gemm_kernel(3 | 4 | 5)  always run the 128 x 256 / 256 x 256 / weights-in-TMEM tcgen05 kernel, 0 = auto
  *   mq_debug_force_hadamard_kernel(1)  CUDA-core Hadamard kernels only (cross-checks), 2 = the
- *                                      previous tensor-core generation for had_k > 1, 0 = auto */
+ *                                      previous tensor-core generation for had_k > 1, 3 = power-of-two
+ *                                      sizes on the mma.sync kernel for every M, 4 = ... on the tcgen05
+ *                                      kernel for every M, 0 = auto */
 int mq_debug_force_gemm_kernel(int kernel);
 int mq_debug_force_hadamard_kernel(int kind);
 

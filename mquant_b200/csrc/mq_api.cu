@@ -83,7 +83,7 @@ EncodeTiledFn get_encode_fn() {
 extern "C" int mq_version(void) { return MQ_VERSION; }
 
 extern "C" int mq_debug_force_hadamard_kernel(int kind) {
-  return mq::g_force_hadamard.exchange(kind == 1 || kind == 2 ? kind : 0);
+  return mq::g_force_hadamard.exchange(kind >= 1 && kind <= 4 ? kind : 0);
 }
 
 extern "C" const char* mq_last_error(void) { return mq::g_err; }

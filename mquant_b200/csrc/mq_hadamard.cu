@@ -343,7 +343,9 @@ static int hadamard_dispatch(const HadArgs& a, cudaStream_t st) {
   int logp = 0;
   while ((1 << logp) < P) ++logp;
   int rc = MQ_ERR_UNSUPPORTED;
-  if (had_k == 1 && fwht_mma_supported(a)) {
+  if (had_k == 1 && hadp2_tc_supported(a)) {
+    rc = launch_hadp2_tc(a, st);  // H_A (x) H_64 on tcgen05, hi / lo split of the intermediate (mq_hadamard_p2.cu)
+  } else if (had_k == 1 && fwht_mma_supported(a)) {
     rc = launch_fwht_mma(a, st);  // 16-point factors on the tensor pipe (mq_hadamard_mma.cu)
   } else if (had_k == 1) {
     switch (logp) {

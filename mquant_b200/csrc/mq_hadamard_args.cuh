@@ -35,4 +35,9 @@ int launch_hadk_tc3(const HadArgs& a, cudaStream_t st);
 bool fwht_mma_supported(const HadArgs& a);
 int launch_fwht_mma(const HadArgs& a, cudaStream_t st);
 
+// mq_hadamard_p2.cu: power-of-two n in {1024 ... 8192}, M >= 1024: both Kronecker factors on tcgen05 with a
+// hi / lo split of the intermediate (fp32 grade); mq_debug_force_hadamard_kernel(3) = off, (4) = for every M
+bool hadp2_tc_supported(const HadArgs& a);
+int launch_hadp2_tc(const HadArgs& a, cudaStream_t st);
+
 }  // namespace mq

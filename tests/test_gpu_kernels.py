@@ -37,6 +37,9 @@ def force(ops):
         def hadamard_tc2(self):  # FWHT in registers + hadK on tcgen05 (second generation)
             lib().mq_debug_force_hadamard_kernel(2)
 
+        def hadamard_pow2(self, kernel):  # power-of-two sizes: "mma" = mma.sync, "tc" = tcgen05, for every M
+            lib().mq_debug_force_hadamard_kernel({"auto": 0, "mma": 3, "tc": 4}[kernel])
+
     yield F()
     lib().mq_debug_force_gemm_kernel(0)
     lib().mq_debug_force_hadamard_kernel(0)
@@ -326,6 +329,31 @@ def test_hadamard_pow2(ops, n):
     s = np.float32(np.float16(np.abs(x.astype(np.float32)).max() / 127 / 4))
     had_check(ops, x, n, 1, s)
     had_check(ops, x, n, 1, s, fp32_had=True)
+
+
+@pytest.mark.parametrize("n,n_in,M", [(1024, 1024, 67), (1024, 960, 5), (2048, 2048, 33), (2048, 1984, 130), (4096, 4096, 37),
+                                      (4096, 3968, 301), (8192, 8192, 19), (8192, 8128, 150), (4096, 4096, 1), (8192, 8192, 2)])
+def test_hadamard_pow2_tcgen05(ops, force, n, n_in, M):
+    """mq_hadamard_p2.cu (H_A (x) H_64 on tcgen05, hi / lo split of the intermediate; the default for
+    M >= 1024) forced for small and ragged token counts: every tile / job tail (tokens past M are
+    zero-filled tiles), zero padding from n_in to n, the split and MSQ variants, and the same
+    tolerance as every other power-of-two kernel (fp32-grade: <= 1 fp16 ulp)."""
+    force.hadamard_pow2("tc")
+    rng = np.random.default_rng(n + M)
+    x = rnd_act(rng, M, n_in)
+    s = np.float32(np.float16(np.abs(x.astype(np.float32)).max() / 127 / 4))
+    y, q = had_check(ops, x, n, 1, s)
+    had_check(ops, x, n, 1, s, split=True)
+    mod = (rng.random(M) < 0.5).astype(np.uint8)
+    had_check(ops, x, n, 1, s, modality=mod, s_vis=np.float32(np.float16(s * 2.5)))
+    # small-magnitude rows (the lo' part of the split must not underflow): 2^-12 x the same data
+    xs = (x.astype(np.float32) * 2.0 ** -12).astype(np.float16)
+    had_check(ops, xs, n, 1, np.float32(np.float16(s * 2.0 ** -12)))
+    # against the mma.sync kernel: identical codes except rare +-1
+    force.hadamard_pow2("mma")
+    _, q2 = had_check(ops, x, n, 1, s)
+    d = np.abs(q.astype(np.int32) - q2.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 2e-3
 
 
 @pytest.mark.parametrize("path", ["default", "tc2", "simt"])
@@ -749,14 +777,17 @@ def test_hadamard_at_benchmark_rows(ops, force, n, n_in):
 
 
 @pytest.mark.parametrize("n", [64, 256, 1024, 4096, 8192])
-def test_hadamard_transform_seam(ops, n):
+def test_hadamard_transform_seam(ops, force, n):
     """mq_hadamard_transform_f16 == fast_hadamard_transform.hadamard_transform(x, scale): any scale,
     strided leading dims (the reference calls it on a transposed view, quant_utils.py:351)."""
     from mquant_b200.fht import hadamard_transform
 
     rng = np.random.default_rng(n)
     x = rnd_act(rng, 50, n)
-    for scale in (1.0, 1.0 / np.sqrt(n), 0.37):
+    for scale in (1.0, 1.0 / np.sqrt(n), 0.37, -0.37):
+        if scale < 0:  # the tcgen05 kernel (default from 1024 rows on) on the same 50 rows
+            force.hadamard_pow2("tc")
+            scale = -scale
         y = host(hadamard_transform(dev(x).reshape(5, 10, n), scale))
         ref = O.fht(x, np.float32(scale)).reshape(5, 10, n)
         d = np.abs(bits16(y).astype(np.int32) - bits16(ref).astype(np.int32))

@@ -155,6 +155,12 @@ def main():
                 sec, best = timeit(lambda: ops.hadamard(x, had_k=K_, hadk=hk, n=n, scales=scales, modality=mod,
                                                         want_codes=True, want_f16=False, fast_had=True))
                 rec(f"hadamard_quant_k{K_}[fast_had]", f"{M}x{n_in}->{n}", sec, best, bytes_=(2 * n_in + n) * M + M)
+            if K_ == 1:  # the previous default (mma.sync, warp per token) on the same input
+                _lib.lib().mq_debug_force_hadamard_kernel(3)
+                sec, best = timeit(lambda: ops.hadamard(x, had_k=K_, hadk=hk, n=n, scales=scales, modality=mod,
+                                                        want_codes=True, want_f16=False))
+                _lib.lib().mq_debug_force_hadamard_kernel(0)
+                rec(f"hadamard_quant_k{K_}[mma.sync]", f"{M}x{n_in}->{n}", sec, best, bytes_=(2 * n_in + n) * M + M)
             del x
 
     if want("gemm"):
