@@ -10,9 +10,9 @@
 //
 //   TMA    tile = 128 rows of 64 elements: the A rows of S = 128 / A ADJACENT tokens (one 3-D box;
 //          rows past n_in / 64 and tokens past M are out of bounds = zero filled)
-//   MMA1   D1[(s,k), j'] = X[(s,k), j] . (H_64 / 64)[j, j']     M = 128, N = 64, K = 64: exact products,
-//          fp32 accumulation; the factor 2^-6 keeps |D1| <= 65504
-//   epi-1  thread = one row (TMEM lane): v = D1 (fp32) is split into hi = fp16(v) and
+//   MMA1   D1[(s,k), j'] = X[(s,k), j] . H_64[j, j']     M = 128, N = 64, K = 64: exact products, fp32
+//          accumulation
+//   epi-1  thread = one row (TMEM lane): v = D1 / 64 (exact, |v| <= 65504) is split into hi = fp16(v) and
 //          lo' = fp16(2^11 (v - hi)) -- |lo'| <= |v|, no underflow before |v| < 2^-35 -- and written as
 //          rows (s,k) and 128 + (s,k) of T, the MN-major B operand of MMA2
 //   MMA2   D2[(s,k'), (p,j')] = (I_S (x) H_A)[(s,k'), (s,k)] . T[(s,k), (p,j')]    M = 128, N = 128 (two
@@ -27,8 +27,8 @@
 //
 // Persistent, one CTA per SM, 512 threads: warps 0-7 second epilogue (set = tile p), 8-11 first
 // epilogue, 12 TMA, 13 MMA1 issuer (+ TMEM allocation), 14 MMA2 issuer.  TMEM: 2 D1 tiles (64 columns
-// each) + 3 D2 jobs (128 columns each).  Shared memory: I_S (x) H_A 32 KB, H_64 8 KB, X ring 3 x 16 KB,
-// T ring 2 x 64 KB.
+// each) + 3 D2 jobs (128 columns each).  Shared memory: I_S (x) H_A 32 KB (its top-left block doubles as
+// H_64 for A >= 64), X ring 4 x 16 KB, T ring 2 x 64 KB.
 // HBM traffic per token: 2*n_in read + n (codes) [+ 2*n fp16].
 #include <cuda.h>
 
@@ -48,21 +48,28 @@ constexpr int EPI2_WARP0 = 0, EPI1_WARP0 = 8, W_TMA = 12, W_MMA1 = 13, W_MMA2 = 
 constexpr int TMEM_COLS = 512;
 constexpr int D1N = 2, D2N = 3;
 constexpr int D2_COL0 = D1N * 64;
-constexpr int XS = 3, TJ = 2;
+constexpr int TJ = 2;
 constexpr int X_SLOT = 128 * 128;      // 128 rows x 64 fp16
 constexpr int T_BLK = 256 * 128;       // one 64-column block of T: 128 hi rows + 128 lo' rows, 128 B each
 constexpr int T_JOB = 2 * T_BLK;
 constexpr int A2_KB = 128 * 128;       // one k-block (64 k) of the A operand: 128 rows x 128 B
-constexpr int SM_A2 = 0;
-constexpr int SM_H = SM_A2 + 2 * A2_KB;
-constexpr int SM_X = SM_H + 64 * 128;
-constexpr int SM_T = SM_X + XS * X_SLOT;
-constexpr int SM_BAR = SM_T + TJ * T_JOB;
-constexpr int NUM_BARS = 2 * XS + 2 * D1N + 2 * TJ + 2 * D2N;
-constexpr int SM_TMEMPTR = SM_BAR + NUM_BARS * 8;
-constexpr int SM_TOTAL = SM_TMEMPTR + 16;
-constexpr int SM_ALLOC = SM_TOTAL + 1024;  // slack to align the window to 1024 bytes (SWIZZLE_128B)
-static_assert(SM_ALLOC <= 227 * 1024, "shared memory budget");
+// For A >= 64 the top-left 64 x 64 block of I_S (x) H_A IS H_64 (rows 0..63 of k-block 0, the same
+// K-major layout): MMA1 reads its B operand there and the 8 KB buy a fourth X slot (loads in flight).
+template <int A>
+struct Lay {
+  static constexpr bool ALIAS_H = A >= 64;
+  static constexpr int XS = ALIAS_H ? 4 : 3;
+  static constexpr int SM_A2 = 0;
+  static constexpr int SM_H = ALIAS_H ? SM_A2 : SM_A2 + 2 * A2_KB;
+  static constexpr int SM_X = SM_A2 + 2 * A2_KB + (ALIAS_H ? 0 : 64 * 128);
+  static constexpr int SM_T = SM_X + XS * X_SLOT;
+  static constexpr int SM_BAR = SM_T + TJ * T_JOB;
+  static constexpr int NUM_BARS = 2 * XS + 2 * D1N + 2 * TJ + 2 * D2N;
+  static constexpr int SM_TMEMPTR = SM_BAR + NUM_BARS * 8;
+  static constexpr int SM_TOTAL = SM_TMEMPTR + 16;
+  static constexpr int SM_ALLOC = SM_TOTAL + 1024;  // slack to align the window to 1024 bytes (SWIZZLE_128B)
+  static_assert(SM_ALLOC <= 227 * 1024, "shared memory budget");
+};
 
 // D = A.B + D * 2^-11
 __device__ __forceinline__ void umma_f16_scale_d11(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
@@ -76,7 +83,8 @@ __device__ __forceinline__ void umma_f16_scale_d11(uint32_t tmem_d, uint64_t ade
 
 // (v0, v1) fp32 -> hi = fp16 pair, lo' = fp16 pair of 2^11 (v - hi)   (v - float(hi) is exact in fp32)
 __device__ __forceinline__ void split_pair(uint32_t b0, uint32_t b1, uint32_t& hi, uint32_t& lo) {
-  const float v0 = __uint_as_float(b0), v1 = __uint_as_float(b1);
+  float v0, v1;  // v = D1 / 64 (exact): |v| <= 65504
+  f2_unpack(f2_mul(f2_pack(__uint_as_float(b0), __uint_as_float(b1)), f2_pack(0.015625f, 0.015625f)), v0, v1);
   hi = f16x2_rn(v0, v1);
   float r0, r1;  // hi - v (mixed-precision subtract: no separate conversion)
   asm("{.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tsub.rn.f32.f16 %0, l, %3;\n\tsub.rn.f32.f16 %1, h, %4;}"
@@ -92,6 +100,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 hadp2_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HadArgs a, const float norm2, const int num_jobs) {
   constexpr int S = 128 / A;  // tokens per tile
   constexpr int JT = 2 * S;   // tokens per job
+  using L = Lay<A>;
+  constexpr int XS = L::XS, SM_A2 = L::SM_A2, SM_H = L::SM_H, SM_X = L::SM_X, SM_T = L::SM_T, SM_BAR = L::SM_BAR,
+                SM_TMEMPTR = L::SM_TMEMPTR;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -141,17 +152,19 @@ hadp2_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HadArgs a, con
   }
   if (warp == W_MMA1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
   {
-    // H_64 / 64 (symmetric): row j', 64 k = 128 B, K-major SWIZZLE_128B; 512 threads = 64 rows x 8 chunks
-    const int row = threadIdx.x >> 3, ch = threadIdx.x & 7;
-    uint32_t w[4];
+    if (!L::ALIAS_H) {
+      // H_64 (symmetric): row j', 64 k = 128 B, K-major SWIZZLE_128B; 512 threads = 64 rows x 8 chunks
+      const int row = threadIdx.x >> 3, ch = threadIdx.x & 7;
+      uint32_t w[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int k0 = ch * 8 + 2 * e;
-      const uint32_t lo = (__popc(row & k0) & 1) ? 0xA400u : 0x2400u;  // -+ 2^-6
-      const uint32_t hi = (__popc(row & (k0 + 1)) & 1) ? 0xA400u : 0x2400u;
-      w[e] = lo | (hi << 16);
+      for (int e = 0; e < 4; ++e) {
+        const int k0 = ch * 8 + 2 * e;
+        const uint32_t lo = (__popc(row & k0) & 1) ? 0xBC00u : 0x3C00u;
+        const uint32_t hi = (__popc(row & (k0 + 1)) & 1) ? 0xBC00u : 0x3C00u;
+        w[e] = lo | (hi << 16);
+      }
+      st_shared_v4(sH + row * 128 + ((uint32_t)(ch ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
     }
-    st_shared_v4(sH + row * 128 + ((uint32_t)(ch ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
     // I_S (x) H_A: [k-block kb][row (s,k')][64 k] K-major SWIZZLE_128B; 128 rows x 16 chunks of 8 k
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
@@ -189,7 +202,7 @@ hadp2_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HadArgs a, con
       }
     }
   } else if (warp == W_MMA1) {
-    // ===================== MMA1 issuer: D1 = X . H64 / 64 ===========================================
+    // ===================== MMA1 issuer: D1 = X . H64 ================================================
     // F16 x F16 -> F32, A K-major, B K-major, M = 128, N = 64
     const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int xs = 0, d1 = 0;
@@ -381,8 +394,8 @@ static int launch(const HadArgs& a, cudaStream_t st) {
   }
   const int num_jobs = (int)((a.M + 2 * S - 1) / (2 * S));
   const int grid = num_jobs < num_sms() ? num_jobs : num_sms();
-  MQ_DYN_SMEM(hadp2_tc_kernel<A>, SM_ALLOC);
-  hadp2_tc_kernel<A><<<grid, NUM_THREADS, SM_ALLOC, st>>>(tmap, a, a.norm * 64.0f, num_jobs);
+  MQ_DYN_SMEM(hadp2_tc_kernel<A>, Lay<A>::SM_ALLOC);
+  hadp2_tc_kernel<A><<<grid, NUM_THREADS, Lay<A>::SM_ALLOC, st>>>(tmap, a, a.norm * 64.0f, num_jobs);
   return MQ_OK;
 }
 

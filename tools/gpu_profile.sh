@@ -4,7 +4,7 @@ R=${1:-r1}
 mkdir -p gpurun_out
 echo "=== launch list (bench, 2 layers): our kernels only, warm-up skipped"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none \
-  -k regex:"w4a8_gemm|act_quant_i8_kernel|hadk_tc|fwht|rmsn" -s 48 -c 16 --csv \
+  -k regex:"w4a8_gemm|act_quant_i8_kernel|hadk_tc|hadp2|fwht|rmsn" -s 48 -c 16 --csv \
   --log-file gpurun_out/launches_${R}.csv python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_${R}.log 2>&1
 tail -1 gpurun_out/launches_${R}.log | cut -c1-200
 echo "=== full: gemm (the 4 shapes of the bench step at M=16384)"
@@ -26,16 +26,17 @@ for K, N in ((4096, 12288), (4096, 4096), (4096, 22016), (11008, 4096), (-4096, 
 PY
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:w4a8_gemm -f -o /tmp/prof_gemm_${R} python /tmp/gemm_shapes.py > gpurun_out/ncu_gemm_${R}.log 2>&1
 python tools/summarize_ncu.py /tmp/prof_gemm_${R}.ncu-rep gpurun_out/${R}_gemm_full.csv
-echo "=== full: hadamard (tc3 K=172, tc2 K=28, mma.sync pow2) + quant + minmax + rmsn + gptq hessian"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"hadk_tc|act_quant_i8_kernel|minmax_tensor_kernel|fwht_|rmsn_quant|hessian_kernel" -c 30 -f -o /tmp/prof_mem_${R} python tools/profile_target.py all 16384 > gpurun_out/ncu_mem_${R}.log 2>&1
+echo "=== full: hadamard (tc3 K=172, tc2 K=28, p2 pow2) + quant + minmax + rmsn + gptq hessian"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"hadk_tc|hadp2_tc|act_quant_i8_kernel|minmax_tensor_kernel|fwht_|rmsn_quant|hessian_kernel" -c 36 -f -o /tmp/prof_mem_${R} python tools/profile_target.py all 16384 > gpurun_out/ncu_mem_${R}.log 2>&1
 tail -2 gpurun_out/ncu_mem_${R}.log
 python tools/summarize_ncu.py /tmp/prof_mem_${R}.ncu-rep gpurun_out/${R}_membound_full.csv
 # (the .ncu-rep files stay on the box: gpurun_out/ is limited to 64 MiB; the per-kernel details pages are text)
-ncu -i /tmp/prof_mem_${R}.ncu-rep --page details -k regex:"hadk_tc3|fwht_mma|rmsn_quant|hessian|w4a8_gemm_v5" 2>/dev/null | grep -v "^    -\+$" > gpurun_out/${R}_membound_details.txt
+ncu -i /tmp/prof_mem_${R}.ncu-rep --page details -k regex:"hadk_tc3|hadp2_tc|fwht_mma|rmsn_quant|hessian|w4a8_gemm_v5" 2>/dev/null | grep -v "^    -\+$" > gpurun_out/${R}_membound_details.txt
 ncu -i /tmp/prof_gemm_${R}.ncu-rep --page details 2>/dev/null | grep -v "^    -\+$" > gpurun_out/${R}_gemm_details.txt
 echo "=== microbench (all)"
 timeout 900 python tools/microbench.py --json gpurun_out/microbench_${R}.json > gpurun_out/microbench_${R}.log 2>&1
 timeout 600 python tools/microbench.py --only hadsweep,gated,gptq --json gpurun_out/microbench2_${R}.json > gpurun_out/microbench2_${R}.log 2>&1
+timeout 400 python tools/had_scaling.py --json gpurun_out/had_scaling_${R}.json > gpurun_out/had_scaling_${R}.log 2>&1
 timeout 600 python tools/latency.py --shapes 4096x4096,4096x12288,4096x22016,11008x4096 --ms 256,1024 --kernels default,v2,v4,v5 > gpurun_out/latency_${R}.log 2>&1
 tail -3 gpurun_out/microbench_${R}.log | cut -c1-200
 echo "=== bench"

@@ -36,6 +36,10 @@ if which in ("had", "all"):
     x = (torch.randn(M, 4096, device="cuda") * 3).half()
     for _ in range(reps):
         ops.hadamard(x, n=4096, scales=scales, modality=mod, want_codes=True, want_f16=False)
+if which in ("had8192", "all"):  # power-of-two sizes: hadp2_tc_kernel (mq_hadamard_p2.cu)
+    x = (torch.randn(M, 8192, device="cuda") * 3).half()
+    for _ in range(reps):
+        ops.hadamard(x, n=8192, scales=scales, modality=mod, want_codes=True, want_f16=False)
 if which in ("had172", "all"):
     x = (torch.randn(M, 11008, device="cuda") * 3).half()
     hk = hu.hadK_device(172, "cuda")
