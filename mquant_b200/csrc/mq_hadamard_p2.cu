@@ -285,14 +285,18 @@ hadp2_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HadArgs a, con
       if (have && want_q && kp == 0 && a.srow_out != nullptr) a.srow_out[tok] = qs.s;
       mbar_wait_sleep(d2_full(d2), d2ph);
       tc_fence_after();
-      if (__any_sync(0xffffffffu, have)) {
+      const bool any = __any_sync(0xffffffffu, have);
+      uint32_t va[32], vb[32];
+      if (any) {
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D2_COL0 + d2 * 128 + set * 64);
-        int8_t* qrow = want_q ? a.q + tok * (int64_t)a.n + (int64_t)kp * 64 : nullptr;
-        __half* yrow = want_y ? a.y + tok * (int64_t)a.n + (int64_t)kp * 64 : nullptr;
-        uint32_t va[32], vb[32];
         tmem_ld32_nowait(taddr, va);
         tmem_ld32_nowait(taddr + 32, vb);
         tmem_wait_ld();
+      }
+      // (the slot is handed back after the quantiser and the stores, see mq_hadamard_tc3.cu)
+      if (any) {
+        int8_t* qrow = want_q ? a.q + tok * (int64_t)a.n + (int64_t)kp * 64 : nullptr;
+        __half* yrow = want_y ? a.y + tok * (int64_t)a.n + (int64_t)kp * 64 : nullptr;
         if (rescale) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
@@ -340,6 +344,9 @@ hadp2_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HadArgs a, con
         tmem_ld32_nowait(taddr, va);
         tmem_ld32_nowait(taddr + 32, vb);
         tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d1_empty(d1));  // the tile is in registers: MMA1 may refill the slot
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t(&v)[32] = half ? vb : va;
@@ -356,10 +363,7 @@ hadp2_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HadArgs a, con
         fence_async_smem();  // T is read by the tensor core (async proxy)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(t_full(tg));
-          mbar_arrive(d1_empty(d1));
-        }
+        if (lane == 0) mbar_arrive(t_full(tg));
         if (++d1 == D1N) { d1 = 0; d1ph ^= 1u; }
       }
       if (++tg == TJ) { tg = 0; tph ^= 1u; }

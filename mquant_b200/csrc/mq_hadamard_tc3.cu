@@ -30,7 +30,7 @@
 //          stores (a warp writes 32 rows x P bytes of one token: contiguous)
 //
 // Persistent, one CTA per SM, 512 threads: warps 0-7 second epilogue (two sets; they first stage
-// hadK while the pipeline fills), warps 8-11 first epilogue (one per TMEM lane quadrant), warp 12
+// hadK together with the first-epilogue warps while the pipeline fills), warps 8-11 first epilogue (one per TMEM lane quadrant), warp 12
 // TMA, warp 13 MMA1 issuer (+ TMEM allocation), warp 14 MMA2 issuer.  TMEM: columns 0..255 ring
 // of D1 tiles, 256..511 two D2 jobs (job = token group x M-tile).
 // HBM traffic per token: 2*n_in read + n (codes) [+ 2*n fp16].
@@ -162,8 +162,18 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
       mbar_init(t_full(s), 4 * c.tpt * G);  // every first-epilogue warp, once per tile of the group's tokens
       mbar_init(t_empty(s), 1);
     }
-    mbar_init(a2_ready, 8);
+    mbar_init(a2_ready, 12);  // the twelve epilogue warps stage hadK
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the first ring of X tiles is requested before the matrices are staged (cold HBM latency)
+    const int pre = min(c.xs, my_tokens * c.tpt);
+    for (int t = 0; t < pre; ++t) {
+      const int lt = t / c.tpt, i = t - lt * c.tpt;
+      const int tok = (int)(blockIdx.x + (int64_t)lt * gridDim.x);
+      mbar_arrive_expect_tx(x_full(t), (uint32_t)c.x_bytes);
+#pragma unroll
+      for (int sub = 0; sub < NS; ++sub)
+        tma_load_3d(sX + t * c.x_bytes + sub * (c.xrows * 128), &tmap_x, 64 * sub, i * c.xrows, tok, x_full(t));
+    }
   }
   if (warp == W_MMA1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
   // H64 (symmetric): row j', 64 k = 128 B, K-major SWIZZLE_128B
@@ -179,28 +189,103 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
     }
     st_shared_v4(sH + row * 128 + ((uint32_t)(ch ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
   }
+  // hadK (the A operand of MMA2) as [k' rows][k] K-major SWIZZLE_128B, zero padded to Kpad x (kb2*64),
+  // k-block kb at kb * Kpad * 128, staged by the twelve epilogue warps.  Before the barrier: the region
+  // is zeroed (the padding) and the first STAGE_WORDS 16-byte words per thread of the flat matrix are
+  // requested -- a cold miss of every CTA of the grid at once takes longer than the rest of the setup
+  // (timeline of the previous version: MMA2 of the first group waited ~9000 cycles for this matrix).
+  // After it: the words are scattered to their swizzled places; a word is two 4-element halves, each
+  // inside one row whenever had_k % 4 == 0.
+  constexpr int STAGERS = 12 * 32, STAGE_WORDS = 10;
+  const bool stager = warp < EPI1_WARP0 + 4;
+  const bool flat_ok = c.expand == 1 && (c.had_k & 3) == 0 && (reinterpret_cast<uintptr_t>(a.hadk) & 15u) == 0;
+  const int nhalf = c.had_k * c.had_k / 4, nword = (nhalf + 1) / 2;
+  uint4 pre[STAGE_WORDS];
+  auto load_word = [&](int w) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* src = reinterpret_cast<const uint4*>(a.hadk);
+    if (2 * w + 1 < nhalf) v = __ldg(src + w);
+    else if (2 * w < nhalf) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(src + w)); v.x = t.x; v.y = t.y; }
+    return v;
+  };
+  if (stager) {
+    if (flat_ok) {
+#pragma unroll
+      for (int u = 0; u < STAGE_WORDS; ++u) pre[u] = load_word((int)threadIdx.x + u * STAGERS);
+    }
+    for (int i = threadIdx.x; i < c.h_off / 16; i += STAGERS) st_shared_v4(sA2 + (uint32_t)i * 16u, 0u, 0u, 0u, 0u);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (stager) {
+    const int tid = threadIdx.x;
+    auto sdst = [&](int row, int k) {
+      return sA2 + (uint32_t)(k >> 6) * (uint32_t)(c.Kpad * 128) + (uint32_t)row * 128u +
+             ((uint32_t)(((k & 63) >> 3) ^ (row & 7)) << 4) + (uint32_t)(k & 7) * 2u;
+    };
+    if (flat_ok) {
+      // row = e / had_k by multiplication: e < 2^16, had_k <= 256 (exact, see mq_common.cuh FastDiv)
+      const uint32_t inv = (uint32_t)((0x100000000ull + (uint32_t)c.had_k - 1) / (uint32_t)c.had_k);
+      auto put_word = [&](int w, const uint4& v) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int e = (2 * w + hf) * 4;  // flat element index of this half
+          if (e < c.had_k * c.had_k) {
+            const int row = (int)__umulhi((uint32_t)e, inv), k = e - row * c.had_k;
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sdst(row, k)), "r"(hf ? v.z : v.x), "r"(hf ? v.w : v.y) : "memory");
+          }
+        }
+      };
+#pragma unroll
+      for (int u = 0; u < STAGE_WORDS; ++u) put_word(tid + u * STAGERS, pre[u]);
+      for (int w0 = tid + STAGE_WORDS * STAGERS; w0 < nword; w0 += STAGE_WORDS * STAGERS) {
+#pragma unroll
+        for (int u = 0; u < STAGE_WORDS; ++u) pre[u] = load_word(w0 + u * STAGERS);
+#pragma unroll
+        for (int u = 0; u < STAGE_WORDS; ++u) put_word(w0 + u * STAGERS, pre[u]);
+      }
+    } else if (c.expand > 1) {
+      // composite factor hadK (x) H_E: element (row, k) = hadK[row / E][k / E] * (-1)^popc((row % E) & (k % E))
+      // (the source matrix is a few hundred elements: L1 hits)
+      const int le = c.expand == 2 ? 1 : c.expand == 4 ? 2 : 3, em = c.expand - 1;
+      for (int e = tid; e < c.had_k * c.had_k; e += STAGERS) {
+        const int row = e / c.had_k, k = e - row * c.had_k;
+        unsigned short v = __half_as_ushort(__ldg(a.hadk + (row >> le) * c.src_k + (k >> le)));
+        if (__popc((row & em) & (k & em)) & 1) v ^= (unsigned short)0x8000u;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(sdst(row, k)), "h"(v) : "memory");
+      }
+    } else {
+      for (int e = tid; e < c.had_k * c.had_k; e += STAGERS) {
+        const int row = e / c.had_k, k = e - row * c.had_k;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(sdst(row, k)), "h"(__half_as_ushort(__ldg(a.hadk + e))) : "memory");
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a2_ready);
+  }
 
   if (warp == W_TMA) {
     // ===================== TMA producer: one tile (NS boxes of xrows x 128 B) per step =============
     if (elect_one()) {
+      // (tiles 0 .. c.xs - 1 were requested during the setup: the ring has wrapped once)
       int xs = 0;
-      uint32_t xph = 0;
-      for (int lt = 0; lt < my_tokens; ++lt) {
+      uint32_t xph = 1;
+      const int total_tiles = my_tokens * c.tpt;
+      int lt = c.xs / c.tpt, i = c.xs - lt * c.tpt;
+      for (int t = c.xs; t < total_tiles; ++t) {
         const int tok = (int)(blockIdx.x + (int64_t)lt * gridDim.x);
-        for (int i = 0; i < c.tpt; ++i) {
-          mbar_wait_sleep(x_empty(xs), xph ^ 1u);
-          mbar_arrive_expect_tx(x_full(xs), (uint32_t)c.x_bytes);
+        mbar_wait_sleep(x_empty(xs), xph ^ 1u);
+        mbar_arrive_expect_tx(x_full(xs), (uint32_t)c.x_bytes);
 #pragma unroll
-          for (int sub = 0; sub < NS; ++sub)
-            tma_load_3d(sX + xs * c.x_bytes + sub * (c.xrows * 128), &tmap_x, 64 * sub, i * c.xrows, tok, x_full(xs));
-          if (i == 0) stamp(lt, 0);
-          if (++xs == c.xs) { xs = 0; xph ^= 1u; }
-        }
+        for (int sub = 0; sub < NS; ++sub)
+          tma_load_3d(sX + xs * c.x_bytes + sub * (c.xrows * 128), &tmap_x, 64 * sub, i * c.xrows, tok, x_full(xs));
+        if (i == 0) stamp(lt, 0);
+        if (++xs == c.xs) { xs = 0; xph ^= 1u; }
+        if (++i == c.tpt) { i = 0; ++lt; }
       }
     }
   } else if (warp == W_MMA1) {
@@ -283,73 +368,6 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
     }
   } else if (warp < EPI2_WARP0 + 8) {
     // ===================== second epilogue: D2 -> fp16 -> fp16 store / INT8 codes -> HBM ==========
-    // First: hadK as [k' rows][k] K-major SWIZZLE_128B, zero padded to Kpad x (kb2*64), k-block kb
-    // at kb * Kpad * 128.  The matrix is read as a flat array of 16-byte words, all loads of a
-    // thread in flight together (one word at a time from its rows took 25 k cycles with every CTA
-    // of the grid missing in L2 at once); a word is two 4-element halves, each inside one row
-    // whenever had_k % 4 == 0.  The padding (columns / rows >= had_k) is zeroed separately.
-    {
-      const int tid = threadIdx.x - EPI2_WARP0 * 32;
-      auto sdst = [&](int row, int k) {
-        return sA2 + (uint32_t)(k >> 6) * (uint32_t)(c.Kpad * 128) + (uint32_t)row * 128u +
-               ((uint32_t)(((k & 63) >> 3) ^ (row & 7)) << 4) + (uint32_t)(k & 7) * 2u;
-      };
-      const int kcols = c.kb2 * 64;
-      if (c.expand > 1) {
-        // composite factor hadK (x) H_E: element (row, k) = hadK[row / E][k / E] * (-1)^popc((row % E) & (k % E))
-        // (the source matrix is a few hundred elements: L1 hits)
-        const int le = c.expand == 2 ? 1 : c.expand == 4 ? 2 : 3, em = c.expand - 1;
-        for (int e = tid; e < c.had_k * c.had_k; e += 256) {
-          const int row = e / c.had_k, k = e - row * c.had_k;
-          unsigned short v = __half_as_ushort(__ldg(a.hadk + (row >> le) * c.src_k + (k >> le)));
-          if (__popc((row & em) & (k & em)) & 1) v ^= (unsigned short)0x8000u;
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(sdst(row, k)), "h"(v) : "memory");
-        }
-      } else if ((c.had_k & 3) == 0 && (reinterpret_cast<uintptr_t>(a.hadk) & 15u) == 0) {
-        const int nhalf = c.had_k * c.had_k / 4, nword = (nhalf + 1) / 2;
-        const uint4* src = reinterpret_cast<const uint4*>(a.hadk);
-        for (int w0 = tid; w0 < nword; w0 += 8 * 256) {
-          uint4 v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int w = w0 + u * 256;
-            v[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (2 * w + 1 < nhalf) v[u] = __ldg(src + w);
-            else if (2 * w < nhalf) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(src + w)); v[u].x = t.x; v[u].y = t.y; }
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int w = w0 + u * 256;
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const int e = (2 * w + hf) * 4;  // flat element index of this half
-              if (e < c.had_k * c.had_k) {
-                const int row = e / c.had_k, k = e - row * c.had_k;
-                asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sdst(row, k)), "r"(hf ? v[u].z : v[u].x), "r"(hf ? v[u].w : v[u].y) : "memory");
-              }
-            }
-          }
-        }
-      } else {
-        for (int e = tid; e < c.had_k * c.had_k; e += 256) {
-          const int row = e / c.had_k, k = e - row * c.had_k;
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(sdst(row, k)), "h"(__half_as_ushort(__ldg(a.hadk + e))) : "memory");
-        }
-      }
-      // zero padding: columns had_k .. kcols-1 of the rows < had_k, whole rows had_k .. Kpad-1
-      const int padc = kcols - c.had_k;
-      for (int id = tid; id < c.had_k * padc; id += 256) {
-        const int row = id / padc, k = c.had_k + (id - row * padc);
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(sdst(row, k)), "h"((unsigned short)0) : "memory");
-      }
-      for (int id = tid; id < (c.Kpad - c.had_k) * (kcols / 8); id += 256) {
-        const int row = c.had_k + id / (kcols / 8), k = (id % (kcols / 8)) * 8;
-        st_shared_v4(sdst(row, k), 0u, 0u, 0u, 0u);
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a2_ready);
-    }
     const int set = (warp - EPI2_WARP0) >> 2, quad = warp & 3;
     const int l = quad * 32 + lane;
     const bool want_q = a.q != nullptr, want_y = a.y != nullptr;
@@ -390,15 +408,19 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
         if (warp == EPI2_WARP0 && mt == 0) stamp(lt, 7);
         if (warp == EPI2_WARP0 + 3 && mt == c.mt - 1) stamp(lt, 9);
         tc_fence_after();
+        uint32_t va[32], vb[32];
+        const int cc0 = G == 2 ? 2 * set : set, cstep = G == 2 ? 1 : 2;  // this set's chunks: cc0, cc0 + cstep
         if (warp_ok) {
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D2_COL0 + d2 * 128);
-          int8_t* qrow = want_q ? a.q + tok * (int64_t)a.n + (int64_t)kp * P : nullptr;
-          __half* yrow = want_y ? a.y + tok * (int64_t)a.n + (int64_t)kp * P : nullptr;
-          const int cc0 = G == 2 ? 2 * set : set, cstep = G == 2 ? 1 : 2;  // this set's chunks: cc0, cc0 + cstep
-          uint32_t va[32], vb[32];
           tmem_ld32_nowait(taddr + cc0 * 32, va);
           tmem_ld32_nowait(taddr + (cc0 + cstep) * 32, vb);
           tmem_wait_ld();
+        }
+        // (the slot is handed back AFTER the quantiser and the stores: releasing it as soon as the columns
+        // are in registers was 7 % SLOWER in a same-box A/B, 130.0 vs 121.8 us at 16384 x 11008)
+        if (warp_ok) {
+          int8_t* qrow = want_q ? a.q + tok * (int64_t)a.n + (int64_t)kp * P : nullptr;
+          __half* yrow = want_y ? a.y + tok * (int64_t)a.n + (int64_t)kp * P : nullptr;
           const int col0 = (G == 2 ? 0 : cc0) * 32, col1 = (G == 2 ? 1 : cc0 + cstep) * 32;  // columns of the token
           const bool first = split && col0 == 0 && kp == 0;
           // (the test for the division-free quantiser is hoisted: inside quant8 it would cut the 64
@@ -411,11 +433,11 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
             epi2_emit<false>(vb, qrow, yrow, col1, qs, lane_ok, false, q32, y32, a.x0_out, tok);
           }
         }
-        tc_fence_before();
-        __syncwarp();
         if (warp == EPI2_WARP0 && mt == 0) stamp(lt, 8);
         if (warp == EPI2_WARP0 + 3 && mt == c.mt - 1) stamp(lt, 10);
         if (G == 2 && mt == 1 && quad >= 2) stamp(g * G + 1, warp == 2 ? 8 : warp == 3 ? 9 : warp == 6 ? 10 : 15);  // (probes: job B done)
+        tc_fence_before();
+        __syncwarp();
         if (lane == 0) mbar_arrive(d2_empty(d2));
         if (++d2 == D2N) { d2 = 0; d2ph ^= 1u; }
       }
