@@ -201,8 +201,8 @@ def measure_int8_library_peak(torch, seconds=1.5):
 
 def run_calibration(torch, dist, dev, rank, world, samples=256):
     """BASELINE configs[2]: W4A8 static calibration of the InternVL2-8B LLM stack (minmax observers,
-    `samples` synthetic image+text samples of 256..2048 tokens, seed 0), samples sharded round-robin
-    over the ranks, statistics merged with ONE allreduce(MAX) (mquant_b200/dist.py), scales derived
+    `samples` synthetic image+text samples of 256..2048 tokens, seed 0), samples sharded over the ranks
+    (equal counts, token-balanced), statistics merged with ONE allreduce(MAX) (mquant_b200/dist.py), scales derived
     from one device-to-host copy.  Timed region = this rank's observer passes + the merge (CUDA
     events, max over ranks).  Strong scaling.  Verified bit-identical to sequential calibration."""
     from mquant_b200 import dist as mqdist, quant_utils
@@ -228,7 +228,7 @@ def run_calibration(torch, dist, dev, rank, world, samples=256):
         for i in indices:
             stk.observe_tokens(sample(i))
 
-    mine = mqdist.shard_indices(samples, rank, world)
+    mine = mqdist.shard_indices(samples, rank, world, weights=lengths)  # equal counts, near-equal tokens per rank
     run(stack, mine[:2])  # warm-up
     mqdist.merge_calibration(stack)
     stack = build()

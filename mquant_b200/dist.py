@@ -19,9 +19,21 @@ from .observer.minmax import MinmaxObserver
 from .quant_utils import ActQuantWrapper, find_qlayers
 
 
-def shard_indices(n_items: int, rank: int, world: int):
-    """Round-robin shard of calibration samples."""
-    return list(range(rank, n_items, world))
+def shard_indices(n_items: int, rank: int, world: int, weights=None):
+    """Shard of calibration samples: round-robin, or -- given per-sample weights such as
+    token counts -- the samples sorted by weight and dealt in serpentine order (ranks 0..w-1, w-1..0, ...):
+    equal counts and near-equal total weight per rank, so no rank waits for another at the merge.  Min/max
+    statistics do not depend on which rank sees which sample."""
+    if weights is None:
+        return list(range(rank, n_items, world))
+    assert len(weights) == n_items
+    order = sorted(range(n_items), key=lambda i: (-weights[i], i))
+    mine = []
+    for pos, i in enumerate(order):
+        rnd, k = divmod(pos, world)
+        if (k if rnd % 2 == 0 else world - 1 - k) == rank:
+            mine.append(i)
+    return sorted(mine)
 
 
 def _minmax_observers(model):

@@ -1024,62 +1024,59 @@ def update_all_quantization_params(model, args=None):
         return len(slow)
     dev = next(o.state.device for q in fast for o in ([q.observer] + ([q.observer_visual] if q.msq else []))
                if o.state is not None)
-    # three concatenations (not one per wrapper: 160 wrappers x a handful of tiny kernels is 10 ms)
+    # three concatenations (not one per wrapper: 160 wrappers x a handful of tiny kernels is 10 ms), and no
+    # per-wrapper tensor indexing on the host: everything below is a handful of vector operations plus
+    # one loop that only stores views (merge of 160 wrappers: 6.3 -> ~2 ms)
+    n = len(fast)
     zero2 = torch.zeros(2, dtype=torch.float32, device=dev)
     t_states = [q.observer.state if q.observer.state is not None else zero2 for q in fast]
     v_states = [q.observer_visual.state if (q.msq and q.observer_visual.state is not None) else zero2 for q in fast]
-    stats = torch.cat(t_states + v_states).cpu().view(2, len(fast), 2)  # ONE copy of all statistics
     counted = [q for q in fast if getattr(q, "_seen", None) is not None]
-    counts = torch.cat([q._seen for q in counted]).cpu().view(-1, 2) if counted else None
-    host = torch.zeros(len(fast), 6)  # {tmin, tmax, vmin, vmax, n_text, n_visual}
-    host[:, 0:2], host[:, 2:4] = stats[0], stats[1]
-    ci = 0
-    for i, q in enumerate(fast):
+    parts = [torch.cat(t_states + v_states)]
+    if counted:
+        parts.append(torch.cat([q._seen for q in counted]).to(torch.float32))  # exact below 2^24 rows
+    flat = torch.cat(parts).cpu()  # ONE copy of all statistics and row counts
+    stats = flat[:4 * n].view(2, n, 2)  # [text | visual][wrapper][min, max]
+    seen_rows = iter(flat[4 * n:].view(-1, 2).tolist())
+    has_t, has_v = [], []
+    for q in fast:
         if getattr(q, "_seen", None) is not None:
-            host[i, 4:6] = counts[ci].float()
-            ci += 1
+            nt, nv = next(seen_rows)
         else:  # (gather path / restored statistics: a state that exists has been seen)
-            host[i, 4] = float(q.observer.state is not None)
-            host[i, 5] = float(q.msq and q.observer_visual.state is not None)
+            nt, nv = float(q.observer.state is not None), float(q.msq and q.observer_visual.state is not None)
+        has_t.append(nt > 0)
+        has_v.append(bool(q.msq) and nv > 0)
     # the reference's expression, in the dtype of the statistics, for all observers at once
     by_dtype = {}
     for i, q in enumerate(fast):
         dt = q.observer._dtype or (q.observer_visual._dtype if q.msq else None) or torch.float16
         by_dtype.setdefault(dt, []).append(i)
     bt = fast[0].observer.bit_type
-    scales = {}
-    for dt, idx in by_dtype.items():
-        h = host[idx]
-        eps = torch.finfo(torch.float32).eps
-        st = torch.max(torch.abs(h[:, 0].to(dt) / bt.lower_bound), torch.abs(h[:, 1].to(dt) / bt.upper_bound)).clamp_(eps)
-        sv = torch.max(torch.abs(h[:, 2].to(dt) / bt.lower_bound), torch.abs(h[:, 3].to(dt) / bt.upper_bound)).clamp_(eps)
-        for j, i in enumerate(idx):
-            scales[i] = (st[j], sv[j])
-    n = len(fast)
-    # text/visual scales of every wrapper as one device tensor; each quantizer keeps views of it
-    host_pairs, dts = [], []
-    for i, q in enumerate(fast):
-        has_t, has_v = bool(host[i, 4] > 0), bool(q.msq and host[i, 5] > 0)
-        st, sv = scales[i]
-        if not has_t and has_v:
-            st = sv  # only visual tokens were ever seen
-        host_pairs.append((st, sv if has_v else st, has_t or has_v, has_v and has_t))
+    eps = torch.finfo(torch.float32).eps
     zp0 = torch.zeros((), dtype=torch.int64, device=dev)
-    for dt in by_dtype:
-        idx = by_dtype[dt]
-        pairs = torch.stack([torch.stack([host_pairs[i][0], host_pairs[i][1]]) for i in idx]).to(dev)  # [m, 2] in dt
+    for dt, idx in by_dtype.items():
+        sel = torch.tensor(idx)
+        h = stats[:, sel, :]
+        st = torch.max(torch.abs(h[0, :, 0].to(dt) / bt.lower_bound), torch.abs(h[0, :, 1].to(dt) / bt.upper_bound)).clamp_(eps)
+        sv = torch.max(torch.abs(h[1, :, 0].to(dt) / bt.lower_bound), torch.abs(h[1, :, 1].to(dt) / bt.upper_bound)).clamp_(eps)
+        ht = torch.tensor([has_t[i] for i in idx])
+        hv = torch.tensor([has_v[i] for i in idx])
+        st = torch.where(~ht & hv, sv, st)  # only visual tokens were ever seen
+        sv = torch.where(hv, sv, st)
+        # text/visual scales of every wrapper as one device tensor; each quantizer keeps views of it
+        pairs = torch.stack([st, sv], 1).to(dev)  # [m, 2] in dt
         f32 = pairs.float().contiguous()
+        s_text, s_vis, s_f32 = pairs[:, 0].unbind(0), pairs[:, 1].unbind(0), f32.unbind(0)
         for j, i in enumerate(idx):
-            q = fast[i]
-            _, _, any_seen, both = host_pairs[i]
-            if not any_seen:
+            if not (has_t[i] or has_v[i]):
                 continue
-            qz = q.quantizer
-            qz.scale = pairs[j, 0]
-            qz.zero_point = zp0
-            has_v = bool(q.msq and host[i, 5] > 0)
-            qz.scale_visual = pairs[j, 1] if has_v else None
-            qz._dev_scales = f32[j]
+            # plain attributes of the quantizer module (never parameters / buffers): stored without
+            # nn.Module.__setattr__'s registry checks
+            d = fast[i].quantizer.__dict__
+            d["scale"] = s_text[j]
+            d["zero_point"] = zp0
+            d["scale_visual"] = s_vis[j] if has_v[i] else None
+            d["_dev_scales"] = s_f32[j]
     return n + len(slow)
 
 

@@ -69,6 +69,15 @@ def test_shard_indices_cover_everything():
     for world in (1, 2, 4, 8):
         got = sorted(i for r in range(world) for i in mqd.shard_indices(256, r, world))
         assert got == list(range(256))
+    # weighted (token-balanced) shards: still a partition, equal counts, near-equal weight per rank
+    rng = np.random.default_rng(0)
+    w = rng.integers(256, 2049, 256).tolist()
+    for world in (2, 4, 8):
+        shards = [mqd.shard_indices(256, r, world, weights=w) for r in range(world)]
+        assert sorted(i for sh in shards for i in sh) == list(range(256))
+        assert {len(sh) for sh in shards} == {256 // world}
+        tot = [sum(w[i] for i in sh) for sh in shards]
+        assert max(tot) - min(tot) <= 2048, tot  # round-robin on this draw: up to ~6 % apart
 
 
 def _worker_model(rank, world, port, ret):
