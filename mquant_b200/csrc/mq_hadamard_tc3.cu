@@ -410,19 +410,17 @@ hadk_tc3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params prm) {
         tc_fence_after();
         uint32_t va[32], vb[32];
         const int cc0 = G == 2 ? 2 * set : set, cstep = G == 2 ? 1 : 2;  // this set's chunks: cc0, cc0 + cstep
-        if (warp_ok) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D2_COL0 + d2 * 128);
-          tmem_ld32_nowait(taddr + cc0 * 32, va);
-          tmem_ld32_nowait(taddr + (cc0 + cstep) * 32, vb);
-          tmem_wait_ld();
-        }
         // (the slot is handed back AFTER the quantiser and the stores: releasing it as soon as the columns
         // are in registers was 7 % SLOWER in a same-box A/B, 130.0 vs 121.8 us at 16384 x 11008)
         if (warp_ok) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(D2_COL0 + d2 * 128);
           int8_t* qrow = want_q ? a.q + tok * (int64_t)a.n + (int64_t)kp * P : nullptr;
           __half* yrow = want_y ? a.y + tok * (int64_t)a.n + (int64_t)kp * P : nullptr;
           const int col0 = (G == 2 ? 0 : cc0) * 32, col1 = (G == 2 ? 1 : cc0 + cstep) * 32;  // columns of the token
           const bool first = split && col0 == 0 && kp == 0;
+          tmem_ld32_nowait(taddr + cc0 * 32, va);
+          tmem_ld32_nowait(taddr + (cc0 + cstep) * 32, vb);
+          tmem_wait_ld();
           // (the test for the division-free quantiser is hoisted: inside quant8 it would cut the 64
           // independent elements of a thread into basic blocks of 8 -- measured IPC 0.19 per warp)
           if (qs.narrow) {

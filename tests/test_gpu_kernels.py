@@ -332,7 +332,8 @@ def test_hadamard_pow2(ops, n):
 
 
 @pytest.mark.parametrize("n,n_in,M", [(1024, 1024, 67), (1024, 960, 5), (2048, 2048, 33), (2048, 1984, 130), (4096, 4096, 37),
-                                      (4096, 3968, 301), (8192, 8192, 19), (8192, 8128, 150), (4096, 4096, 1), (8192, 8192, 2)])
+                                      (4096, 3968, 301), (8192, 8192, 19), (8192, 8128, 150), (4096, 4096, 1), (8192, 8192, 2),
+                                      (4096, 3968, 1031), (2048, 2048, 1500)])
 def test_hadamard_pow2_tcgen05(ops, force, n, n_in, M):
     """mq_hadamard_p2.cu (H_A (x) H_64 on tcgen05, hi / lo split of the intermediate; the default for
     M >= 1024) forced for small and ragged token counts: every tile / job tail (tokens past M are
