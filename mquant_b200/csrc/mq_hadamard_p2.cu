@@ -25,8 +25,8 @@
 //          rounding point) -> fp16 store and / or the exact INT8 quantiser with the token's MSQ scale ->
 //          256-bit stores (a warp writes 32 rows x 64 outputs of a token: contiguous)
 //
-// Persistent, one CTA per SM, 512 threads: warps 0-7 second epilogue (set = tile p), 8-11 first
-// epilogue, 12 TMA, 13 MMA1 issuer (+ TMEM allocation), 14 MMA2 issuer.  TMEM: 2 D1 tiles (64 columns
+// Persistent, one CTA per SM, 512 threads: warps 0-3 first epilogue, 4-11 second epilogue (set = tile
+// p), 12 TMA, 13 MMA1 issuer (+ TMEM allocation), 14 MMA2 issuer.  TMEM: 2 D1 tiles (64 columns
 // each) + 3 D2 jobs (128 columns each).  Shared memory: I_S (x) H_A 32 KB (its top-left block doubles as
 // H_64 for A >= 64), X ring 4 x 16 KB, T ring 2 x 64 KB.
 // HBM traffic per token: 2*n_in read + n (codes) [+ 2*n fp16].
@@ -43,8 +43,8 @@ using namespace mq::tc;
 using namespace mq::hadepi;
 
 constexpr int NUM_THREADS = 512;
-// issuers at the highest warp ids, the heavy second epilogue at the lowest (see mq_hadamard_tc3.cu)
-constexpr int EPI2_WARP0 = 0, EPI1_WARP0 = 8, W_TMA = 12, W_MMA1 = 13, W_MMA2 = 14;
+// issuers at the highest warp ids, then the second epilogue, the first epilogue lowest (see mq_hadamard_tc3.cu)
+constexpr int EPI1_WARP0 = 0, EPI2_WARP0 = 4, W_TMA = 12, W_MMA1 = 13, W_MMA2 = 14;
 constexpr int TMEM_COLS = 512;
 constexpr int D1N = 2, D2N = 3;
 constexpr int D2_COL0 = D1N * 64;
@@ -254,7 +254,7 @@ hadp2_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HadArgs a, con
       if (++d2 == D2N) { d2 = 0; d2ph ^= 1u; }
       if (++tg == TJ) { tg = 0; tph ^= 1u; }
     }
-  } else if (warp < EPI2_WARP0 + 8) {
+  } else if (warp >= EPI2_WARP0 && warp < EPI2_WARP0 + 8) {
     // ===================== second epilogue: D2 -> * 64 norm -> fp16 -> fp16 store / INT8 codes -> HBM
     const int set = (warp - EPI2_WARP0) >> 2, quad = warp & 3;
     const int l = quad * 32 + lane;
@@ -324,7 +324,7 @@ hadp2_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const HadArgs a, con
       if (lane == 0) mbar_arrive(d2_empty(d2));
       if (++d2 == D2N) { d2 = 0; d2ph ^= 1u; }
     }
-  } else if (warp < EPI1_WARP0 + 4) {
+  } else if (warp >= EPI1_WARP0 && warp < EPI1_WARP0 + 4) {
     // ===================== first epilogue: D1 -> hi / lo' rows of T ===================================
     const int quad = warp & 3;
     const int l = quad * 32 + lane;
