@@ -42,14 +42,18 @@ static int plan_kernel(int64_t M, int64_t N, int64_t K, size_t workspace_bytes) 
   const int64_t n_tiles = (N + BN - 1) / BN, k_tiles = K / BK;
   const bool gemv_shape = M <= 8 || (M <= 16 && n_tiles < 32);
   if (gemv_shape && workspace_bytes > 0 && workspace_bytes >= gemv_workspace_bytes(N)) return 1;
-  // Wave model fitted to tools/latency.py (hot code, cold weights; us per wave of one tile per SM, K in
-  // k-blocks; profiles/r2_gemm_latency.log): 256 x 256 tiles 0.60 K + 7.5, 128 x 256 (weights in TMEM)
-  // 0.35 K + 6.5, a split-K item 0.55 K/split + 6.5 + 8 for the reduction.
+  // Wave model fitted to tools/latency.py (hot code, cold weights; us, K in k-blocks;
+  // profiles/r2m_gemm_latency.log).  A persistent CTA overlaps the loads of its next tile with the
+  // epilogue of the current one, so the first wave costs more than each further one:
+  //   256 x 256 tiles                     first 0.60 K + 5.5    further 0.60 K + 3.3
+  //   128 x 256 tiles (weights in TMEM)   first 0.28 K + 11.4   further 0.28 K + 5.6
+  //   a split-K item                      0.55 K/split + 6.5 + 8 for the reduction
+  // (one 1024-token request: q|k|v = 2 waves of the first kernel, 47 us, against 3 of the second, 50 us)
   const int64_t sms = num_sms();
   const int64_t waves4 = (((M + 255) / 256) * n_tiles + sms - 1) / sms;
   const int64_t waves5 = (((M + 255) / 256) * ((N + 127) / 128) + sms - 1) / sms;
-  const double cost4 = (double)waves4 * (0.60 * k_tiles + 7.5);
-  const double cost5 = (double)waves5 * (0.35 * k_tiles + 6.5);
+  const double cost4 = 0.60 * k_tiles + 5.5 + (double)(waves4 - 1) * (0.60 * k_tiles + 3.3);
+  const double cost5 = 0.28 * k_tiles + 11.4 + (double)(waves5 - 1) * (0.28 * k_tiles + 5.6);
   int best = cost4 < cost5 ? 4 : 5;
   const double cost = cost4 < cost5 ? cost4 : cost5;
   const int split = splitk_factor(M, N, K);
