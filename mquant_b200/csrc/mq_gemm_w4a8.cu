@@ -47,7 +47,7 @@ static int plan_kernel(int64_t M, int64_t N, int64_t K, size_t workspace_bytes) 
   // epilogue of the current one, so the first wave costs more than each further one:
   //   256 x 256 tiles                     first 0.60 K + 5.5    further 0.60 K + 3.3
   //   128 x 256 tiles (weights in TMEM)   first 0.28 K + 11.4   further 0.28 K + 5.6
-  //   a split-K item                      0.55 K/split + 6.5 + 8 for the reduction
+  //   a split-K item                      0.44 K/split + 17 (9 of it the reduction)
   // (one 1024-token request: q|k|v = 2 waves of the first kernel, 47 us, against 3 of the second, 50 us)
   const int64_t sms = num_sms();
   const int64_t waves4 = (((M + 255) / 256) * n_tiles + sms - 1) / sms;
@@ -58,7 +58,7 @@ static int plan_kernel(int64_t M, int64_t N, int64_t K, size_t workspace_bytes) 
   const double cost = cost4 < cost5 ? cost4 : cost5;
   const int split = splitk_factor(M, N, K);
   if (workspace_bytes > 0 && split >= 2 && workspace_bytes >= splitk_workspace_bytes(M, N, K)) {
-    const double cost_sk = 0.55 * (double)((k_tiles + split - 1) / split) + 14.5;
+    const double cost_sk = 0.44 * (double)((k_tiles + split - 1) / split) + 17.0;
     if (cost_sk < cost) best = 2;
   }
   return best;
