@@ -164,30 +164,60 @@ minmax_tensor_msq_kernel(const __half* __restrict__ x, int64_t ldx, int64_t M, i
   }
 }
 
-// channel_wise: io = {min[C], max[C]}.  blockIdx.x -> 2048-channel slab (256 threads x 8
-// channels), blockIdx.y -> row slice; each thread keeps its 8 channels in registers.
+// channel_wise: io = {min[C], max[C]}.  blockIdx.x -> 256-channel slab (32 lanes x 8 channels: a warp
+// reads 512 contiguous bytes of a row), the 8 warps of a CTA take different rows (blockIdx.y -> row
+// slice), 4 independent 128-bit loads in flight per thread; the warps' partial results meet in shared
+// memory and the CTA issues ONE pair of atomics per channel.  (The first version kept 2048 channels per
+// CTA and one row in flight per thread, and every thread merged its 8 channels with 16 global atomics:
+// 4.8 M atomics on 8192 words for 16384 x 4096 -- 0.25 of HBM.)
 __global__ void __launch_bounds__(256)
 minmax_channel_kernel(const __half* __restrict__ x, int64_t ldx, int64_t M, int C, float* __restrict__ io) {
-  const int col = (blockIdx.x * 256 + threadIdx.x) << 3;
-  if (col >= C) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + lane) << 3;
+  const bool col_ok = col < C;
   __half2 mx[4], mn[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) mx[i] = mn[i] = __float2half2_rn(0.f);
-  for (int64_t m = blockIdx.y; m < M; m += gridDim.y) {
-    const uint4 v = ldg_stream(x + m * ldx + col);
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
+  const int64_t row0 = (int64_t)blockIdx.y * 8 + w, step = (int64_t)gridDim.y * 8;
+  if (col_ok) {
+    for (int64_t m = row0; m < M; m += 4 * step) {
+      uint4 v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      mx[i] = __hmax2(mx[i], h[i]);
-      mn[i] = __hmin2(mn[i], h[i]);
+      for (int u = 0; u < 4; ++u) {
+        const int64_t r = m + u * step;
+        v[u] = r < M ? ldg_stream(x + r * ldx + col) : make_uint4(0u, 0u, 0u, 0u);  // (0 is the neutral start value)
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          mx[i] = __hmax2(mx[i], h[i]);
+          mn[i] = __hmin2(mn[i], h[i]);
+        }
+      }
     }
   }
+  __shared__ __half2 smx[8][32][4], smn[8][32][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    merge_min(io + col + 2 * i, __low2float(mn[i]));
-    merge_min(io + col + 2 * i + 1, __high2float(mn[i]));
-    merge_max(io + C + col + 2 * i, __low2float(mx[i]));
-    merge_max(io + C + col + 2 * i + 1, __high2float(mx[i]));
+    smx[w][lane][i] = mx[i];
+    smn[w][lane][i] = mn[i];
+  }
+  __syncthreads();
+  // thread t finishes channel t of the slab: column t / 8 (lane), element t % 8
+  const int t = threadIdx.x, ln = t >> 3, e = t & 7;
+  const int ch = blockIdx.x * 256 + t;
+  if (ch < C) {
+    float fmx = 0.f, fmn = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) {
+      const __half2 a = smx[ww][ln][e >> 1], b = smn[ww][ln][e >> 1];
+      fmx = fmaxf(fmx, (e & 1) ? __high2float(a) : __low2float(a));
+      fmn = fminf(fmn, (e & 1) ? __high2float(b) : __low2float(b));
+    }
+    merge_min(io + ch, fmn);
+    merge_max(io + C + ch, fmx);
   }
 }
 
@@ -375,10 +405,11 @@ extern "C" int mq_observer_minmax(const void* x, int64_t ldx, int64_t M, int C, 
     if (blocks > cap) blocks = cap;
     minmax_tensor_kernel<<<(int)blocks, 256, 0, st>>>((const __half*)x, ldx, M, C, minmax_io);
   } else {
-    const int slabs = (C + 2047) / 2048;
-    int64_t slices = ((int64_t)num_sms() * 8 + slabs - 1) / slabs;
-    if (slices > M) slices = M;
+    const int slabs = (C + 255) / 256;
+    int64_t slices = ((int64_t)num_sms() * 8 + slabs - 1) / slabs;  // ~8 CTAs per SM in total
+    if (slices > (M + 7) / 8) slices = (M + 7) / 8;
     if (slices > 65535) slices = 65535;
+    if (slices < 1) slices = 1;
     dim3 grid(slabs, (unsigned)slices);
     minmax_channel_kernel<<<grid, 256, 0, st>>>((const __half*)x, ldx, M, C, minmax_io);
   }
