@@ -166,6 +166,105 @@ act_quant_i8_dynamic_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* _
   }
 }
 
+// Same contract with the row held in REGISTERS between the two phases (one HBM read, no re-read through
+// L1 / L2): WPT warps share a token, a thread owns up to 8 units of 16 consecutive elements (two 128-bit
+// loads, all of them in flight together), min / max meet by shuffles and -- for WPT > 1 -- in shared
+// memory.  NU = 4 units per thread wherever 8 warps can hold the row that way (~70 registers, three CTAs
+// per SM; with 8 units and one warp per 4096-wide token the kernel was SLOWER than the two-pass one: 16
+// warps per SM do not hide the quantiser behind the loads).  Rows up to 32768 elements; the kernel above
+// serves anything wider.
+template <int WPT, int NU>
+__global__ void __launch_bounds__(256)
+act_quant_i8_dynamic_reg_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* __restrict__ q,
+                                float* __restrict__ srow_out, int64_t M, int n_in, int n_out, float clip_ratio) {
+  constexpr int TPC = 8 / WPT;  // tokens per CTA pass
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int tslot = w / WPT, wsub = w % WPT;
+  const int units = n_out >> 4;
+  __shared__ float smx[8], smn[8];
+  const int64_t passes = (M + TPC - 1) / TPC;
+  for (int64_t pass = blockIdx.x; pass < passes; pass += gridDim.x) {
+    const int64_t m = pass * TPC + tslot;
+    const bool row_ok = m < M;
+    const __half* xr = x + m * ldx;
+    uint4 v[NU][2];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      const int col = (wsub * 32 + lane + j * 32 * WPT) << 4;
+      v[j][0] = (row_ok && col + 8 <= n_in) ? ldg_stream(xr + col) : make_uint4(0u, 0u, 0u, 0u);
+      v[j][1] = (row_ok && col + 16 <= n_in) ? ldg_stream(xr + col + 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __half2 mx = __float2half2_rn(0.f), mn = __float2half2_rn(0.f);
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[j][h2]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          mx = __hmax2(mx, h[i]);
+          mn = __hmin2(mn, h[i]);
+        }
+      }
+    }
+    float fmx = fmaxf(__low2float(mx), __high2float(mx));
+    float fmn = fminf(__low2float(mn), __high2float(mn));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      fmx = fmaxf(fmx, __shfl_xor_sync(0xffffffffu, fmx, o));
+      fmn = fminf(fmn, __shfl_xor_sync(0xffffffffu, fmn, o));
+    }
+    if (WPT > 1) {
+      if (lane == 0) {
+        smx[w] = fmx;
+        smn[w] = fmn;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < WPT; ++i) {
+        fmx = fmaxf(fmx, smx[tslot * WPT + i]);
+        fmn = fminf(fmn, smn[tslot * WPT + i]);
+      }
+      __syncthreads();  // (the slots are rewritten in the next pass)
+    }
+    // quant_utils.py:240-247: xmin/xmax (with 0) * clip_ratio in fp32, xmax = max(|xmin|, xmax),
+    // scale = xmax / maxq, all-zero rows -> 1
+    const float xmin = __fmul_rn(fmn, clip_ratio), xmax0 = __fmul_rn(fmx, clip_ratio);
+    const float xmax = fmaxf(fabsf(xmin), xmax0);
+    const float s = (xmax == 0.f) ? 1.f : __fdiv_rn(xmax, 127.f);
+    if (row_ok && wsub == 0 && lane == 0) srow_out[m] = s;
+    const QScale qs = make_qscale(s);
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      const int u = wsub * 32 + lane + j * 32 * WPT;
+      if (row_ok && u < units) {
+        const int col = u << 4;
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (col + 8 <= n_in) {
+          const uint2 r = quant8_bracket(v[j][0], qs);
+          out.x = r.x;
+          out.y = r.y;
+        }
+        if (col + 16 <= n_in) {
+          const uint2 r = quant8_bracket(v[j][1], qs);
+          out.z = r.x;
+          out.w = r.y;
+        }
+        stg_stream(q + m * (int64_t)n_out + col, out);
+      }
+    }
+  }
+}
+
+template <int WPT, int NU>
+static void launch_dynamic_reg(const __half* x, int64_t ldx, int8_t* q, float* srow_out, int64_t M, int n_in, int n_out,
+                               float clip_ratio, cudaStream_t st) {
+  const int64_t passes = (M + (8 / WPT) - 1) / (8 / WPT);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  const int grid = (int)(passes < cap ? passes : cap);
+  act_quant_i8_dynamic_reg_kernel<WPT, NU><<<grid, 256, 0, st>>>(x, ldx, q, srow_out, M, n_in, n_out, clip_ratio);
+}
+
 static int grid_for(int64_t work_items, int threads, int per_sm) {
   int64_t blocks = (work_items + threads - 1) / threads;
   int64_t cap = (int64_t)num_sms() * per_sm;
@@ -233,6 +332,19 @@ extern "C" int mq_act_quant_i8_dynamic(const void* x, int64_t ldx, int8_t* q, fl
              (long long)ldx);
   MQ_REQUIRE(mq::aligned16(x) && mq::aligned16(q), "mq_act_quant_i8_dynamic: pointers must be 16-byte aligned");
   if (M == 0) return MQ_OK;
+  const int units = n_out / 16;
+  if (units <= 32 * 8 * 8) {
+    // the row stays in registers: as few warps per token as hold it in 4 units per thread
+    const __half* xh = (const __half*)x;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (units <= 128) mq::launch_dynamic_reg<1, 4>(xh, ldx, q, srow_out, M, n_in, n_out, clip_ratio, st);
+    else if (units <= 256) mq::launch_dynamic_reg<2, 4>(xh, ldx, q, srow_out, M, n_in, n_out, clip_ratio, st);
+    else if (units <= 512) mq::launch_dynamic_reg<4, 4>(xh, ldx, q, srow_out, M, n_in, n_out, clip_ratio, st);
+    else if (units <= 1024) mq::launch_dynamic_reg<8, 4>(xh, ldx, q, srow_out, M, n_in, n_out, clip_ratio, st);
+    else mq::launch_dynamic_reg<8, 8>(xh, ldx, q, srow_out, M, n_in, n_out, clip_ratio, st);
+    MQ_LAUNCH_CHECK("act_quant_i8_dynamic_reg_kernel");
+    return MQ_OK;
+  }
   const int grid = mq::grid_for(M * 32, 256, 8);
   mq::act_quant_i8_dynamic_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, q, srow_out,
                                                                           M, n_in, n_out, clip_ratio);
