@@ -79,12 +79,81 @@ act_quant_i8_kernel(const __half* __restrict__ x, int64_t ldx, int8_t* __restric
   }
 }
 
+// INT8 fake quantisation with fp16- / bf16-valued scales (every MinmaxObserver scale): the codes of the
+// division-free quantiser (quant2_narrow, mq_common.cuh) never leave the fp32 domain -- the packed sum of
+// the two bracket ends is 2 (M + code), so code = sum / 2 - M exactly -- and are dequantised with the
+// reference's expression fp16(fp32(code) * s).  A zero result takes the sign of x + 0 (torch.round keeps
+// the sign of a tiny negative quotient, "+ zero_point" turns -0 into +0).  ~6 instructions per element
+// against ~14 of the generic kernel below; same results bit for bit.
+__device__ __forceinline__ uint4 fake8_narrow(const uint4& v, const QNarrow& q, uint64_t s2) {
+  uint4 out;
+  uint32_t* o = reinterpret_cast<uint32_t*>(&out);
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+  uint64_t magic2, half2_, negm2;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(magic2) : "f"(MQ_RND_MAGIC));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(half2_) : "f"(0.5f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(negm2) : "f"(-MQ_RND_MAGIC));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 xz = __hadd2(h[i], __float2half2_rn(0.f));  // -0 -> +0, everything else unchanged
+    const float2 f = __half22float2(__hmin2(__hmax2(h[i], q.lim_lo), q.lim_hi));
+    uint64_t x, lo, hi, sum, c, y;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(f.x), "f"(f.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(lo) : "l"(x), "l"(q.inv_lo2), "l"(magic2));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(hi) : "l"(x), "l"(q.inv_hi2), "l"(magic2));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(sum) : "l"(lo), "l"(hi));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(c) : "l"(sum), "l"(half2_), "l"(negm2));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(y) : "l"(c), "l"(s2));
+    float y0, y1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(y));
+    const __half2 r = __floats2half2_rn(y0, y1);
+    o[i] = *reinterpret_cast<const uint32_t*>(&r) | (*reinterpret_cast<const uint32_t*>(&xz) & 0x80008000u);
+  }
+  return out;
+}
+
+__device__ __forceinline__ void fake_i8_narrow_body(const __half* __restrict__ x, int64_t ldx, __half* __restrict__ y,
+                                                    int64_t ldy, const uint8_t* __restrict__ modality,
+                                                    const QScale& q_text, const QScale& q_vis, uint32_t total,
+                                                    const FastDiv& cpr) {
+  const QNarrow n_text = make_qnarrow(q_text), n_vis = make_qnarrow(q_vis);
+  uint64_t s2_text, s2_vis;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(s2_text) : "f"(q_text.s));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(s2_vis) : "f"(q_vis.s));
+  const uint32_t stride = gridDim.x * blockDim.x;
+  // work item = one 16-byte chunk; four of them (64 B of loads) in flight per thread
+  for (uint32_t c0 = blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += stride * 4) {
+    uint4 v[4];
+    uint32_t row[4];
+    int col[4];
+    bool vis[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t c = c0 + u * stride;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      row[u] = 0;
+      col[u] = 0;
+      vis[u] = false;
+      if (c < total) {
+        row[u] = cpr.div(c);
+        col[u] = (int)(c - row[u] * cpr.d) << 3;
+        v[u] = ldg_stream(x + (int64_t)row[u] * ldx + col[u]);
+        vis[u] = (modality != nullptr) && (__ldg(modality + row[u]) != 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (c0 + u * stride >= total) break;
+      stg_stream(y + (int64_t)row[u] * ldy + col[u], fake8_narrow(v[u], vis[u] ? n_vis : n_text, vis[u] ? s2_vis : s2_text));
+    }
+  }
+}
+
 // scale_mode 0: per-token scale by modality; 1: per-channel scale array
 template <int kScaleMode>
-__global__ void __launch_bounds__(256)
-act_fake_quant_kernel(const __half* __restrict__ x, int64_t ldx, __half* __restrict__ y, int64_t ldy,
-                      const uint8_t* __restrict__ modality, const float* __restrict__ scales,
-                      float lo, float hi, int64_t M, int C) {
+__device__ __forceinline__ void fake_generic_body(const __half* __restrict__ x, int64_t ldx, __half* __restrict__ y,
+                                                  int64_t ldy, const uint8_t* __restrict__ modality,
+                                                  const float* __restrict__ scales, float lo, float hi, int64_t M, int C) {
   const int chunks_per_row = C >> 3;
   const int64_t total = M * chunks_per_row;
   float s_text = 0.f, s_vis = 0.f;
@@ -113,6 +182,27 @@ act_fake_quant_kernel(const __half* __restrict__ x, int64_t ldx, __half* __restr
     }
     stg_stream(y + m * ldy + col, pack8_f16(f));
   }
+}
+
+template <int kScaleMode>
+__global__ void __launch_bounds__(256)
+act_fake_quant_kernel(const __half* __restrict__ x, int64_t ldx, __half* __restrict__ y, int64_t ldy,
+                      const uint8_t* __restrict__ modality, const float* __restrict__ scales,
+                      float lo, float hi, int64_t M, int C) {
+  fake_generic_body<kScaleMode>(x, ldx, y, ldy, modality, scales, lo, hi, M, C);
+}
+
+// INT8, per-token scale by modality: the division-free body when both scales are fp16- / bf16-valued
+// (they live in device memory, so the choice is made here, once per kernel), else the generic one
+__global__ void __launch_bounds__(256)
+act_fake_quant_i8_kernel(const __half* __restrict__ x, int64_t ldx, __half* __restrict__ y, int64_t ldy,
+                         const uint8_t* __restrict__ modality, const float* __restrict__ scales, uint32_t total,
+                         FastDiv cpr, int64_t M, int C) {
+  const QScale q_text = make_qscale(__ldg(scales)), q_vis = make_qscale(__ldg(scales + 1));
+  if (q_text.narrow && q_vis.narrow)
+    fake_i8_narrow_body(x, ldx, y, ldy, modality, q_text, q_vis, total, cpr);
+  else
+    fake_generic_body<0>(x, ldx, y, ldy, modality, scales, -128.f, 127.f, M, C);
 }
 
 // One warp per token row: pass 1 min/max (row stays in L1/L2), pass 2 quantise.
@@ -312,6 +402,12 @@ extern "C" int mq_act_fake_quant_f16(const void* x, int64_t ldx, void* y, int64_
   const float lo = -(float)(1 << (bits - 1)), hi = (float)((1 << (bits - 1)) - 1);
   const int64_t chunks = M * (C / 8);
   const int grid = mq::grid_for(chunks, 256, 8);
+  if (scale_mode == 0 && bits == 8 && chunks < (1ll << 31)) {
+    mq::act_fake_quant_i8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, ldx, (__half*)y, ldy, modality, scales, (uint32_t)chunks, mq::FastDiv((uint32_t)(C / 8)), M, C);
+    MQ_LAUNCH_CHECK("act_fake_quant_i8_kernel");
+    return MQ_OK;
+  }
   if (scale_mode == 0)
     mq::act_fake_quant_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const __half*)x, ldx, (__half*)y, ldy, modality, scales, lo, hi, M, C);

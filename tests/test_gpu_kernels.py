@@ -126,6 +126,26 @@ def test_act_quant_every_fp16_value(ops):
         assert np.array_equal(host(q), O.act_quant_codes(x, s).astype(np.int8)), s
 
 
+def test_fake_quant_every_fp16_value(ops):
+    """INT8 fake quantisation, exhaustive over the input domain (every finite fp16 value of either sign,
+    so also +-0 and the tiny negatives whose result is -0): fp16-valued scales take the division-free
+    kernel (act_fake_quant_i8_kernel), the others the generic one; with a modality mask both scales of
+    a call are exercised.  Bit-exact against the oracle, signs of zero included."""
+    vals = np.arange(0, 0x7C00, dtype=np.uint16).view(np.float16)
+    x = np.concatenate([vals, -vals]).reshape(-1, 64)
+    mod = (np.arange(x.shape[0]) % 3 == 0).astype(np.uint8)
+    for s_t, s_v in ((0.25, 0.0731), (1.0, 3.0517578125e-05), (0.61865234375, 117.5), (0.0213, 0.0571)):
+        if s_t != 0.0213:  # (the last pair is not fp16-valued: generic kernel)
+            s_t, s_v = np.float32(np.float16(s_t)), np.float32(np.float16(s_v))
+        else:
+            s_t, s_v = np.float32(s_t), np.float32(s_v)
+        y = host(ops.act_fake_quant(dev(x), ops.make_scales(float(s_t), float(s_v), "cuda"), dev(mod)))
+        ref = np.where(mod[:, None] != 0, O.act_fake_quant(x, s_v), O.act_fake_quant(x, s_t))
+        assert np.array_equal(bits16(y), bits16(ref)), (s_t, s_v)
+        y1 = host(ops.act_fake_quant(dev(x), ops.make_scales(float(s_t), device="cuda")))
+        assert np.array_equal(bits16(y1), bits16(O.act_fake_quant(x, s_t))), s_t
+
+
 @pytest.mark.parametrize("bits", [8, 16])
 def test_fake_quant(ops, golden, bits):
     g = golden("act_quant")
