@@ -27,7 +27,7 @@ PY
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:w4a8_gemm -f -o /tmp/prof_gemm_${R} python /tmp/gemm_shapes.py > gpurun_out/ncu_gemm_${R}.log 2>&1
 python tools/summarize_ncu.py /tmp/prof_gemm_${R}.ncu-rep gpurun_out/${R}_gemm_full.csv
 echo "=== full: hadamard (tc3 K=172, tc2 K=28, p2 pow2) + quant + minmax + rmsn + gptq hessian"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"hadk_tc|hadp2_tc|act_quant_i8_kernel|minmax_tensor_kernel|fwht_|rmsn_quant|hessian_kernel" -c 36 -f -o /tmp/prof_mem_${R} python tools/profile_target.py all 16384 > gpurun_out/ncu_mem_${R}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"hadk_tc|hadp2_tc|act_quant_i8_kernel|act_fake_quant_i8|act_quant_i8_dynamic|minmax_tensor_kernel|minmax_channel|fwht_|rmsn_quant|hessian_kernel" -c 48 -f -o /tmp/prof_mem_${R} python tools/profile_target.py all 16384 > gpurun_out/ncu_mem_${R}.log 2>&1
 tail -2 gpurun_out/ncu_mem_${R}.log
 python tools/summarize_ncu.py /tmp/prof_mem_${R}.ncu-rep gpurun_out/${R}_membound_full.csv
 # (the .ncu-rep files stay on the box: gpurun_out/ is limited to 64 MiB; the per-kernel details pages are text)

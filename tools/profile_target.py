@@ -50,6 +50,13 @@ if which in ("had28", "all"):  # InternVL2-8B feed_forward.w2: 14336 = 28 x 512 
     hk = hu.hadK_device(28, "cuda")
     for _ in range(reps):
         ops.hadamard(x, had_k=28, hadk=hk, n=14336, scales=scales, modality=mod, want_codes=True, want_f16=False)
+if which in ("fake", "all"):  # the op of an un-frozen wrapper: INT8 fake quantisation, per-token dynamic quantiser, channel-wise min/max
+    x = (torch.randn(M, 4096, device="cuda") * 3).half()
+    stc = torch.zeros(2 * 4096, device="cuda")
+    for _ in range(reps):
+        ops.act_fake_quant(x, scales, mod)
+        ops.act_quant_i8_dynamic(x)
+        ops.observer_minmax(x, stc, True)
 if which in ("rmsn", "all"):
     x = (torch.randn(M, 4096, device="cuda") * 3).half()
     for _ in range(reps):
