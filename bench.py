@@ -447,14 +447,33 @@ def main():
         gemm_launches[0] += 1
         return r
 
+    # ... and every launch of kernel (a) of the north star, the fused online Hadamard + INT8 quantiser
+    # (HBM bound: algorithmic bytes = 2 B read per input element + 1 B per code written + 1 B per token mask)
+    had_ev, had_bytes = [], [0]
+    orig_had = ops.hadamard
+
+    def timed_had(x, *args, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_had(x, *args, **kw)
+        e1.record()
+        had_ev.append((e0, e1))
+        rows = x.numel() // x.shape[-1]
+        had_bytes[0] += rows * (2 * x.shape[-1] + (r["q"].shape[-1] if r.get("q") is not None else 0)
+                                + (2 * r["y"].shape[-1] if r.get("y") is not None else 0) + 1)
+        return r
+
     import mquant_b200.quant_utils as _qu
     _qu.ops.w4a8_gemm = timed_gemm
+    _qu.ops.hadamard = timed_had
     try:
         stack.forward_tokens(inputs)
         torch.cuda.synchronize()
         gemm_total_ms = sum(e0.elapsed_time(e1) for e0, e1 in gemm_ms)
+        had_total_ms = sum(e0.elapsed_time(e1) for e0, e1 in had_ev)
     finally:
         _qu.ops.w4a8_gemm = orig
+        _qu.ops.hadamard = orig_had
     n_gemm = gemm_launches[0]
     gemm_ops = stack.gemm_ops_per_token() * a.tokens
     achieved = gemm_ops / (gemm_total_ms * 1e-3) / 1e12
@@ -495,6 +514,19 @@ def main():
                 "avg_launch_ms": gemm_total_ms / max(n_gemm, 1), "launches_timed": n_gemm,
                 "share_of_step": gemm_total_ms / ms_step}
 
+    hbm_peak = float(pk.get("hbm_gbs", 6650.0))
+    roofline_hadamard = None
+    if had_ev:
+        had_gbs = had_bytes[0] / (had_total_ms * 1e-3) / 1e9
+        roofline_hadamard = {"bound": "hbm", "kernel": "fused online Hadamard + INT8 quantiser (hadk_tc3_kernel / hadp2_tc_kernel)",
+                             "achieved": had_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": had_gbs / hbm_peak,
+                             "peak_source": "hbm_gbs of MEASURED_PEAKS.json" if "hbm_gbs" in pk else "fallback 6650 GB/s (B200_PROFILING.md)",
+                             "avg_launch_ms": had_total_ms / len(had_ev), "launches_timed": len(had_ev),
+                             "algorithmic_bytes_per_launch": had_bytes[0] / len(had_ev),
+                             "share_of_step": had_total_ms / ms_step, "traffic": None,
+                             "note": "timed inside the power-capped step (the kernel is issue / latency bound, so it follows the SM "
+                                     "clock: ~1.55 GHz here); a lone launch reaches 0.68-0.69 of HBM at this shape and 0.75 in "
+                                     "steady state (tools/microbench.py --only hadsweep, tools/had_scaling.py, profiles/r2p_*)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -516,6 +548,7 @@ def main():
                             "step i computes; one input copy + one result read-back per timed step"},
         "gpu_launches": stack.launches_per_step() * a.steps,
         "roofline": roofline,
+        "roofline_hadamard": roofline_hadamard,
     }
     if not a.no_calibration:
         del stack, inputs, e2e_inputs, one
