@@ -28,7 +28,7 @@
 // Persistent, one CTA per SM, 512 threads: warps 0-3 first epilogue, 4-11 second epilogue (set = tile
 // p), 12 TMA, 13 MMA1 issuer (+ TMEM allocation), 14 MMA2 issuer.  TMEM: 2 D1 tiles (64 columns
 // each) + 3 D2 jobs (128 columns each).  Shared memory: I_S (x) H_A 32 KB (its top-left block doubles as
-// H_64 for A >= 64), X ring 4 x 16 KB, T ring 2 x 64 KB.
+// H_64 for A >= 64; A < 64 keeps a separate 8 KB H_64), X ring 4 x 16 KB (3 for A < 64), T ring 2 x 64 KB.
 // HBM traffic per token: 2*n_in read + n (codes) [+ 2*n fp16].
 #include <cuda.h>
 
